@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's kernel micro-benchmark (kernel/dgl-new.py) on a reddit-shaped
+synthetic graph, through the drop-in API (dgl.ops.gspmm / dgl.ops.gsddmm) into the sm_100a kernels.
+
+One STEP = one pass of the hot path over the workload of BASELINE.json configs[1]:
+    for D in (64, 128, 256, 602):   gspmm(g, copy_lhs, sum, X_D)   and   gsddmm(g, dot, X_D, V_D)
+on a uniform random multigraph with reddit's shape (232 965 nodes, 11 606 919 edges, edge order
+shuffled so the CSC edge-id permutation is non-trivial), fp32, int32 ids.
+
+metric  = algorithmic HBM GB/s of the sweep: sum over the 8 launches of the gather-model bytes of
+          SURVEY.md section 8(d) / DESIGN.md, divided by the step time.
+value   = device-resident inputs (CUDA events around K steps, max over ranks).
+e2e     = same sweep through the same API with HOST inputs: every step copies X_D, V_D from pinned
+          host memory and reads both results back to pinned host memory inside the timed region.
+roofline= the dominant kernel (gspmm copy_u_sum, D=602): bytes / its average duration measured with
+          CUDA events around that launch inside the timed region, vs MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline / --impl reference = the CPU oracle (C/OpenMP restatement of DGL v0.6.1's CPU kernels;
+          DGL itself cannot be installed here) on a bounded sample of the same workload.
+
+N > 1 (torchrun): every rank holds the whole graph structure and owns a contiguous, nnz-balanced
+range of destination rows (1-D row partition) and the matching rows of X; each op first all-gathers
+the source features over NCCL, then aggregates its own rows.  Total work is fixed: "strong".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "dgl-0.5-benchmark_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+N_NODES, N_EDGES = 232965, 11606919
+WIDTHS = (64, 128, 256, 602)
+METRIC = "gspmm copy_u_sum + gsddmm u_dot_v algorithmic HBM GB/s (reddit-shaped, D=64..602)"
+
+
+# ------------------------------------------------------------------ algorithmic bytes
+def spmm_bytes(n_dst, n_edges, D, s=4):
+    return 4 * (n_dst + 1) + 4 * n_edges + s * D * n_edges + s * D * n_dst
+
+
+def sddmm_dot_bytes(n_dst, n_edges, D, s=4, p=1):
+    return 4 * (n_dst + 1) + 4 * n_edges + 4 * p * n_edges + s * D * n_edges + s * D * n_dst + s * n_edges
+
+
+def step_bytes(n_dst, n_edges, p=1):
+    return sum(spmm_bytes(n_dst, n_edges, D) + sddmm_dot_bytes(n_dst, n_edges, D, p=p) for D in WIDTHS)
+
+
+# ------------------------------------------------------------------ clocks sampling
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = []
+        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(s[3 + i].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_arm(steps, warmup, budget_s=20.0):
+    """Times the CPU oracle (all host threads) on a bounded sample of the workload: the first R
+    destination rows of the CSC for gspmm and the first M edges for gsddmm, full D sweep."""
+    from oracle import dgl_ref as R
+    from dgl.data import synthetic
+    import ctypes
+    R.build()
+    cores = R.num_threads()
+    src, dst = synthetic.random_edges(N_NODES, N_NODES, N_EDGES, seed=0)
+    og = R.OracleGraph(src, dst, N_NODES, N_NODES)
+    indptr, indices, eids = og.csc
+    rng = np.random.default_rng(0)
+    feats = {D: (rng.random((N_NODES, D), dtype=np.float32), rng.random((N_NODES, D), dtype=np.float32)) for D in WIDTHS}
+    lib = R.lib()
+
+    def run_sample(rows, edges):
+        for D in WIDTHS:
+            X, V = feats[D]
+            out = np.empty((rows, D), np.float32)
+            lib.oracle_spmm_csr(4, 0, ctypes.c_int64(rows), R._p(indptr), R._p(indices), R._p(eids), R._p(X), None,
+                                ctypes.c_int64(D), ctypes.c_int64(D), ctypes.c_int64(D), None, None, R._p(out), None, None)
+            o2 = np.empty((edges, 1), np.float32)
+            lib.oracle_sddmm_coo(6, 0, 2, ctypes.c_int64(edges), R._p(og.src), R._p(og.dst), R._p(X), R._p(V),
+                                 ctypes.c_int64(D), ctypes.c_int64(D), ctypes.c_int64(1), ctypes.c_int64(D), None, None, R._p(o2))
+
+    def sample_bytes(rows, edges):
+        e_rows = int(indptr[rows])
+        return sum(spmm_bytes(rows, e_rows, D) + (4 * edges * 2 + 4 * D * edges * 2 + 4 * edges) for D in WIDTHS)
+
+    # calibrate on 1/64 of the rows / edges, then size the sample for ~budget_s/(steps+warmup) per step
+    r0, m0 = N_NODES // 64, N_EDGES // 64
+    t0 = time.perf_counter(); run_sample(r0, m0); t_cal = time.perf_counter() - t0
+    per_step = budget_s / max(steps + warmup, 1)
+    scale = max(1.0 / 64, min(1.0, per_step / max(t_cal * 64, 1e-9)))
+    rows, edges = max(1, int(N_NODES * scale)), max(1, int(N_EDGES * scale))
+    for _ in range(warmup):
+        run_sample(rows, edges)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run_sample(rows, edges)
+    dt = (time.perf_counter() - t0) / steps
+    gbs = sample_bytes(rows, edges) / dt / 1e9
+    return {"value": gbs, "unit": "GB/s", "cores": cores, "kind": "port",
+            "sample": "first %d dst rows (gspmm, CSC order) and first %d edges (gsddmm COO) of the reddit-shaped graph, "
+                      "D sweep %s, %.2f s per step; DGL itself is not installable here: C/OpenMP restatement" %
+                      (rows, edges, list(WIDTHS), dt)}, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "reddit-shaped uniform random multigraph N=232965 E=11606919 (shuffled edge order), "
+                          "gspmm copy_u_sum + gsddmm u_dot_v, D in {64,128,256,602}, fp32/int32",
+              "l2": "no explicit flush: the sweep touches 2.0 GB of features per step, >> 126 MB L2, between reuses"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, dt = cpu_arm(args.steps, max(args.warmup, 1))
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import dgl
+    from dgl import _capi
+    from dgl.data import synthetic
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- workload (structure identical on every rank; rows are partitioned for N > 1)
+    src, dst = synthetic.random_edges(N_NODES, N_NODES, N_EDGES, seed=0)
+    if world > 1:
+        from dgl.distributed_rows import RowPartition
+        part = RowPartition.build(src, dst, N_NODES, world, rank, dev)
+        g = part.local_graph
+        n_dst_local, n_edges_local = part.n_local_rows, part.n_local_edges
+    else:
+        part = None
+        g = dgl.graph((torch.from_numpy(src), torch.from_numpy(dst)), num_nodes=N_NODES).int().to(dev)
+        n_dst_local, n_edges_local = N_NODES, N_EDGES
+    torch.manual_seed(rank)
+    feats = {}
+    for D in WIDTHS:
+        rows = n_dst_local if part is not None else N_NODES
+        feats[D] = (torch.rand(rows, D, device=dev), torch.rand(rows, D, device=dev))
+    host = None
+
+    ev = {"spmm602": []}
+
+    def one_step(record=False):
+        for D in WIDTHS:
+            X, V = feats[D]
+            if part is not None:
+                Xfull = part.all_gather_rows(X)
+            else:
+                Xfull = X
+            if record and D == 602:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+            out = dgl.ops.gspmm(g, "copy_lhs", "sum", Xfull, None)
+            if record and D == 602:
+                b.record()
+                ev["spmm602"].append((a, b))
+            sc = dgl.ops.gsddmm(g, "dot", Xfull, V)
+        return out, sc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        one_step()  # builds CSC (cold start, as the reference's 2 cold reps do)
+        for _ in range(args.warmup):
+            one_step()
+        barrier()
+        l0 = _capi.launches()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clocks:
+            start.record()
+            for _ in range(args.steps):
+                one_step(record=True)
+            end.record()
+            barrier()
+        ms = start.elapsed_time(end) / args.steps
+        launches = _capi.launches() - l0
+        k_ms = float(np.mean([a.elapsed_time(b) for a, b in ev["spmm602"]]))
+
+        # ---- e2e: host inputs, H2D + compute + D2H inside the timed region (public API)
+        rows = n_dst_local if part is not None else N_NODES
+        host = {D: (torch.rand(rows, D).pin_memory(), torch.rand(rows, D).pin_memory()) for D in WIDTHS}
+        host_out = {D: (torch.empty(n_dst_local, D).pin_memory(), torch.empty(n_edges_local, 1).pin_memory()) for D in WIDTHS}
+        h2d = sum(2 * rows * D * 4 for D in WIDTHS)
+        d2h = sum(n_dst_local * D * 4 + n_edges_local * 4 for D in WIDTHS)
+
+        def e2e_step():
+            for D in WIDTHS:
+                X = host[D][0].to(dev, non_blocking=True)
+                V = host[D][1].to(dev, non_blocking=True)
+                Xfull = part.all_gather_rows(X) if part is not None else X
+                out = dgl.ops.gspmm(g, "copy_lhs", "sum", Xfull, None)
+                sc = dgl.ops.gsddmm(g, "dot", Xfull, V)
+                host_out[D][0].copy_(out, non_blocking=True)
+                host_out[D][1].copy_(sc, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e_steps = max(3, args.steps // 2)
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for _ in range(e_steps):
+            e2e_step()
+        e2.record()
+        barrier()
+        e2e_ms = s2.elapsed_time(e2) / e_steps
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([ms, e2e_ms, k_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_ms, k_ms = tt.tolist()
+        cnt = torch.tensor([float(launches)], device=dev, dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        launches = int(cnt.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_bytes = step_bytes(N_NODES, N_EDGES, p=1)
+    value = total_bytes / (ms * 1e-3) / 1e9
+    e2e_val = total_bytes / (e2e_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    kb = spmm_bytes(n_dst_local, n_edges_local, 602)
+    achieved = kb / (k_ms * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "roofline": {"bound": "hbm", "kernel": "spmm_rows_kernel<VEC=2,CH=4,copy_lhs,sum> (gspmm copy_u_sum, D=602)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_launch": kb},
+            "e2e": {"value": e2e_val, "unit": "GB/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
+            "gpu_launches": launches, "clocks": clocks.summary(),
+            "edges_per_s": 8 * N_EDGES / (ms * 1e-3)}
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_arm(1, 0, budget_s=15.0)
+        line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

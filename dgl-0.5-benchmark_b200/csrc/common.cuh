@@ -1,0 +1,114 @@
+// common.cuh -- shared helpers for the sm_100a sparse message-passing kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/dglb200.h"
+
+namespace dglb {
+
+// ------------------------------------------------------------------ error plumbing
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define DGLB_CHECK_ARG(cond, ...)      \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::dglb::set_error(__VA_ARGS__);  \
+      return DGLB_E_INVALID;           \
+    }                                  \
+  } while (0)
+
+#define DGLB_CUDA(call)                                            \
+  do {                                                             \
+    cudaError_t e__ = (call);                                      \
+    if (e__ != cudaSuccess) return ::dglb::cuda_fail(e__, #call);  \
+  } while (0)
+
+#define DGLB_LAUNCH_CHECK(name)                                       \
+  do {                                                                \
+    cudaError_t e__ = cudaGetLastError();                             \
+    if (e__ != cudaSuccess) return ::dglb::cuda_fail(e__, name);      \
+  } while (0)
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+constexpr int kBlockThreads = 256;
+
+// ------------------------------------------------------------------ small vectors of floats
+template <int VEC>
+struct FVec {
+  float v[VEC];
+};
+
+// read-only (non-coherent) vector load of VEC consecutive floats; p must be VEC*4-byte aligned
+template <int VEC>
+__device__ __forceinline__ FVec<VEC> ldg_vec(const float* p) {
+  FVec<VEC> r;
+  if constexpr (VEC == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else if constexpr (VEC == 2) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    r.v[0] = t.x; r.v[1] = t.y;
+  } else {
+    r.v[0] = __ldg(p);
+  }
+  return r;
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_vec(float* p, const FVec<VEC>& r) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(r.v[0], r.v[1]);
+  } else {
+    *p = r.v[0];
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void st_vec_i32(int32_t* p, const int32_t (&r)[VEC]) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<int4*>(p) = make_int4(r[0], r[1], r[2], r[3]);
+  } else if constexpr (VEC == 2) {
+    *reinterpret_cast<int2*>(p) = make_int2(r[0], r[1]);
+  } else {
+    *p = r[0];
+  }
+}
+
+// ------------------------------------------------------------------ host-side launch geometry
+// Lanes per row ("group"): the smallest power of two >= ncols (vector columns), capped at 32.
+inline int group_lanes(int64_t ncols) {
+  int g = 1;
+  while (g < 32 && g < ncols) g <<= 1;
+  return g;
+}
+
+// widest vector width (floats) usable for rows of `len` floats starting at `ptr`
+inline int pick_vec(int64_t len, const void* ptr) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(ptr);
+  if (len % 4 == 0 && a % 16 == 0) return 4;
+  if (len % 2 == 0 && a % 8 == 0) return 2;
+  return 1;
+}
+
+inline int min_int(int a, int b) { return a < b ? a : b; }
+
+// right-aligned broadcast description of two trailing feature shapes
+struct BcastShape {
+  int ndim;
+  int64_t lhs[DGLB_MAX_BCAST_NDIM], rhs[DGLB_MAX_BCAST_NDIM], out[DGLB_MAX_BCAST_NDIM];
+  int64_t lhs_len, rhs_len, out_len;
+};
+
+// returns 0 on success; fills b.  For op DOT the last axis is the reduction axis: out's last
+// dim is 1 and *reduce_size receives its length.
+int make_bcast(int op, int ndim, const int64_t* lhs_shape, const int64_t* rhs_shape, BcastShape* b,
+               int64_t* reduce_size);
+
+}  // namespace dglb

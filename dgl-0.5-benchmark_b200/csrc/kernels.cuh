@@ -1,0 +1,77 @@
+// kernels.cuh -- parameter blocks and entry points shared between capi.cu and the kernel
+// translation units.
+#pragma once
+#include "common.cuh"
+
+namespace dglb {
+
+struct GenericSddmmParams {
+  // COO form: src/dst by edge id.  CSR form: indptr/indices/eids (row found by binary search).
+  const int32_t* src;
+  const int32_t* dst;
+  const int32_t* indptr;
+  const int32_t* indices;
+  const int32_t* eids;
+  const float* L;
+  const float* R;
+  float* out;
+  int64_t nnz, n_rows;
+  int op, lhs_target, rhs_target;
+  int64_t reduce_size;
+  BcastShape b;
+};
+
+struct GatParams {
+  const int32_t* __restrict__ indptr;
+  const int32_t* __restrict__ indices;  // neighbour ids (src for CSC, dst for CSR)
+  const int32_t* __restrict__ eids;     // edge ids (dropout counter, edge_scores); null = position
+  const float* __restrict__ ft;         // (n_src, H, F)
+  const float* __restrict__ el;         // (n_src, H)
+  const float* __restrict__ er;         // (n_dst, H)
+  const float* __restrict__ row_max;    // (n_dst, H)   (fwd: written)
+  const float* __restrict__ row_sum;
+  const float* __restrict__ s1;         // (n_dst, H)   (bwd_src: read)
+  const float* __restrict__ dZ;         // (n_dst, H, F) grad of rst
+  float* __restrict__ out_feat;         // fwd: rst (n_dst,H,F); bwd_src: grad_ft (n_src,H,F)
+  float* __restrict__ out_h0;           // fwd: row_max; bwd_dst: s1;      bwd_src: grad_el
+  float* __restrict__ out_h1;           // fwd: row_sum; bwd_dst: grad_er
+  float* __restrict__ edge_scores;      // fwd only, may be null
+  const int32_t* __restrict__ hub_rows;
+  int64_t n_rows;
+  int H, F, D;  // D = H*F
+  int ncols;    // D / VEC
+  int G, log2G;
+  int hub_threshold;
+  float slope;
+  float drop_p, drop_scale;  // drop_scale = 1/(1-p)
+  uint32_t seed_lo, seed_hi;
+};
+
+// graph_build.cu
+size_t coo_to_csr_workspace_bytes(int64_t n_rows, int64_t nnz);
+int coo_to_csr(int64_t n_rows, int64_t nnz, const int32_t* row, const int32_t* col, int32_t* indptr,
+               int32_t* indices, int32_t* data, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int csr_degrees(int64_t n_rows, const int32_t* indptr, int32_t* deg, cudaStream_t stream);
+int is_identity_perm(int64_t n, const int32_t* data, int32_t* flag, cudaStream_t stream);
+int csr_find_hub_rows(int64_t n_rows, const int32_t* indptr, int32_t threshold, int32_t* hub_rows,
+                      int64_t cap, int32_t* n_hub, cudaStream_t stream);
+// spmm.cu
+int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* indptr,
+                 const int32_t* indices, const int32_t* eids, const float* X, const float* W,
+                 const BcastShape& b, float* out, int32_t* arg_u, int32_t* arg_e, const float* row_scale,
+                 const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold, cudaStream_t stream);
+// sddmm.cu
+int sddmm_csr_fast_f32(int op, int64_t n_dst, const int32_t* indptr, const int32_t* indices,
+                       const int32_t* eids, const float* Uf, const float* Vf, const BcastShape& b,
+                       int64_t reduce_size, float* out, const int32_t* hub_rows, int32_t n_hub,
+                       int32_t hub_threshold, cudaStream_t stream);
+int sddmm_generic_f32(const GenericSddmmParams& g, cudaStream_t stream);
+// edge_softmax.cu
+int edge_softmax_f32(bool bwd, int64_t n_dst, int64_t n_heads, const int32_t* indptr, const int32_t* eids,
+                     const float* a, const float* b, float* out, const int32_t* hub_rows, int32_t n_hub,
+                     int32_t hub_threshold, cudaStream_t stream);
+// gat_fused.cu  (which: 0 fwd, 1 bwd_dst, 2 bwd_src)
+int gat_fused_f32(int which, GatParams& p, int64_t H, int64_t F, float dropout_p, uint64_t seed,
+                  int32_t n_hub, int32_t hub_threshold, cudaStream_t stream);
+
+}  // namespace dglb

@@ -1,0 +1,392 @@
+// sddmm.cu -- generalized SDDMM (per-edge op of a source-node and a destination-node row),
+// hand-written for sm_100a.
+//
+// Replaces upstream DGL v0.6.1 src/array/cuda/sddmm.cuh (SDDMMCooKernel: a thread-row per edge,
+// TWO random row gathers per edge and a sequential per-thread dot; SDDMMCsrKernel: the same plus a
+// per-edge binary search) behind `_CAPI_DGLKernelSDDMM`; reached from kernel/dgl-new.py:39 and
+// from GATConv (u_add_v forward, u_dot_v in the backward of u_mul_e_sum).
+//
+// Design: destination-major traversal of the CSC.  A group of G lanes owns one destination row,
+// keeps that row's V tile in registers and streams the row's in-edges: per edge only the source
+// row is gathered (half the gather traffic of the edge-parallel form).  `dot` partial products
+// are reduced across the group with warp shuffles (segmented by head for (N,H,F) operands) and
+// written to out[eid]; elementwise ops store the combined row at out[eid,:].  Hub rows get one
+// CTA each whose groups split the row's edges (no combine step is needed).  Shapes the vector
+// path does not cover use a generic thread-per-(edge,feature) kernel (COO or CSR form).
+#include "kernels.cuh"
+
+namespace dglb {
+
+struct SddmmParams {
+  const int32_t* __restrict__ indptr;
+  const int32_t* __restrict__ indices;
+  const int32_t* __restrict__ eids;
+  const float* __restrict__ U;  // lhs rows gathered by source id
+  const float* __restrict__ V;  // rhs rows, one per destination row
+  float* __restrict__ out;
+  const int32_t* __restrict__ hub_rows;
+  int64_t n_rows;
+  int D;      // floats per node row
+  int ncols;  // D / VEC
+  int G, log2G;
+  int H;      // dot: number of output columns (heads)
+  int seg;    // dot: lanes per head
+  int hub_threshold;
+};
+
+template <int OP>
+__device__ __forceinline__ float ew_op(float l, float r) {
+  if constexpr (OP == DGLB_OP_ADD) return __fadd_rn(l, r);
+  else if constexpr (OP == DGLB_OP_SUB) return __fsub_rn(l, r);
+  else if constexpr (OP == DGLB_OP_MUL) return __fmul_rn(l, r);
+  else if constexpr (OP == DGLB_OP_DIV) return __fdiv_rn(l, r);
+  else if constexpr (OP == DGLB_OP_COPY_LHS) return l;
+  else return r;
+}
+
+// (row, first CSR position, count) of the calling group; HUB: CTA per hub row, groups take slices
+template <bool HUB>
+__device__ __forceinline__ void group_work(const SddmmParams& p, int64_t& row, int64_t& j0, int& n) {
+  if constexpr (!HUB) {
+    row = ((int64_t)blockIdx.x * kBlockThreads + threadIdx.x) >> p.log2G;
+    j0 = 0; n = 0;
+    if (row < p.n_rows) {
+      const int s = __ldg(p.indptr + row);
+      const int d = __ldg(p.indptr + row + 1) - s;
+      if (d <= p.hub_threshold) { j0 = s; n = d; }
+    } else {
+      row = 0;
+    }
+  } else {
+    row = p.hub_rows[blockIdx.x];
+    const int n_groups = kBlockThreads >> p.log2G;
+    const int gidx = threadIdx.x >> p.log2G;
+    const int s = __ldg(p.indptr + row);
+    const int d = __ldg(p.indptr + row + 1) - s;
+    const int per = (d + n_groups - 1) / n_groups;
+    const int b = min(gidx * per, d);
+    j0 = (int64_t)s + b;
+    n = min(per, d - b);
+  }
+}
+
+// ------------------------------------------------------------------ dot
+template <int VEC, int CH, bool HUB>
+__global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmParams p) {
+  constexpr int U = 8 / CH;
+  const int G = p.G;
+  const int lg = threadIdx.x & (G - 1);
+  int64_t row, j0;
+  int n;
+  group_work<HUB>(p, row, j0, n);
+  const int nmax = __reduce_max_sync(FULL_MASK, n);
+  const int tile_cols = G * CH;
+  const bool single = p.ncols <= tile_cols;
+  const float* __restrict__ vrow = p.V + row * (int64_t)p.D;
+  FVec<VEC> vreg[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) vreg[c].v[v] = 0.f;
+    const int vc = c * G + lg;
+    if (single && n > 0 && vc < p.ncols) vreg[c] = ldg_vec<VEC>(vrow + vc * VEC);
+  }
+  for (int off = 0; off < nmax; off += G) {
+    const int m = min(max(n - off, 0), G);
+    int my_c = 0, my_e = 0;
+    if (lg < m) {
+      const int64_t j = j0 + off + lg;
+      my_c = __ldg(p.indices + j);
+      my_e = p.eids ? __ldg(p.eids + j) : (int)j;
+    }
+    const int mmax = min(G, nmax - off);
+    for (int t = 0; t < mmax; t += U) {
+      int cc[U], ee[U];
+      float part[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        cc[u] = __shfl_sync(FULL_MASK, my_c, t + u, G);
+        ee[u] = __shfl_sync(FULL_MASK, my_e, t + u, G);
+        part[u] = 0.f;
+      }
+      for (int tile0 = 0; tile0 < p.ncols; tile0 += tile_cols) {
+        FVec<VEC> xv[U][CH];
+        FVec<VEC> vv[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int vc = tile0 + c * G + lg;
+          if (single) vv[c] = vreg[c];
+          else if (vc < p.ncols && m > 0) vv[c] = ldg_vec<VEC>(vrow + vc * VEC);
+          else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) vv[c].v[v] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool valid = (t + u) < m;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const int vc = tile0 + c * G + lg;
+            if (valid && vc < p.ncols) {
+              xv[u][c] = ldg_vec<VEC>(p.U + (int64_t)cc[u] * p.D + vc * VEC);
+            } else {
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) xv[u][c].v[v] = 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int c = 0; c < CH; ++c)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) part[u] = fmaf(xv[u][c].v[v], vv[c].v[v], part[u]);
+      }
+      // segmented butterfly: seg lanes per head (seg == G when there is one head)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        for (int s = p.seg >> 1; s > 0; s >>= 1) part[u] += __shfl_xor_sync(FULL_MASK, part[u], s);
+        if ((t + u) < m && (lg & (p.seg - 1)) == 0 && (lg / p.seg) < p.H)
+          p.out[(int64_t)ee[u] * p.H + (lg / p.seg)] = part[u];
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ elementwise, full shapes
+template <int VEC, int CH, int OP, bool HUB>
+__global__ void __launch_bounds__(kBlockThreads) sddmm_ew_kernel(const SddmmParams p) {
+  constexpr int U = 8 / CH;
+  constexpr bool USE_L = OP != DGLB_OP_COPY_RHS;
+  constexpr bool USE_R = OP != DGLB_OP_COPY_LHS;
+  const int G = p.G;
+  const int lg = threadIdx.x & (G - 1);
+  int64_t row, j0;
+  int n;
+  group_work<HUB>(p, row, j0, n);
+  const int nmax = __reduce_max_sync(FULL_MASK, n);
+  const float* __restrict__ vrow = p.V + row * (int64_t)p.D;
+  for (int tile0 = 0; tile0 < p.ncols; tile0 += G * CH) {
+    FVec<VEC> vreg[CH];
+    bool colv[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int vc = tile0 + c * G + lg;
+      colv[c] = vc < p.ncols;
+      if (USE_R && colv[c] && n > 0) vreg[c] = ldg_vec<VEC>(vrow + vc * VEC);
+    }
+    for (int off = 0; off < nmax; off += G) {
+      const int m = min(max(n - off, 0), G);
+      int my_c = 0, my_e = 0;
+      if (lg < m) {
+        const int64_t j = j0 + off + lg;
+        if (USE_L) my_c = __ldg(p.indices + j);
+        my_e = p.eids ? __ldg(p.eids + j) : (int)j;
+      }
+      const int mmax = min(G, nmax - off);
+      for (int t = 0; t < mmax; t += U) {
+        int cc[U], ee[U];
+        FVec<VEC> xv[U][CH];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          cc[u] = USE_L ? __shfl_sync(FULL_MASK, my_c, t + u, G) : 0;
+          ee[u] = __shfl_sync(FULL_MASK, my_e, t + u, G);
+        }
+        if constexpr (USE_L) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const bool valid = (t + u) < m;
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+              if (valid && colv[c])
+                xv[u][c] = ldg_vec<VEC>(p.U + (int64_t)cc[u] * p.D + (tile0 + c * G + lg) * VEC);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const bool valid = (t + u) < m;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            if (valid && colv[c]) {
+              FVec<VEC> o;
+#pragma unroll
+              for (int v = 0; v < VEC; ++v)
+                o.v[v] = ew_op<OP>(USE_L ? xv[u][c].v[v] : 0.f, USE_R ? vreg[c].v[v] : 0.f);
+              st_vec<VEC>(p.out + (int64_t)ee[u] * p.D + (tile0 + c * G + lg) * VEC, o);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ generic (any target / broadcast)
+
+__global__ void __launch_bounds__(kBlockThreads) sddmm_generic_kernel(const GenericSddmmParams p) {
+  const int64_t idx = (int64_t)blockIdx.x * kBlockThreads + threadIdx.x;
+  const int64_t OL = p.b.out_len;
+  if (idx >= p.nnz * OL) return;
+  const int64_t pos = idx / OL;
+  int64_t rem = idx - pos * OL;
+  int64_t s, d, e;
+  if (p.src) {
+    e = pos; s = p.src[pos]; d = p.dst[pos];
+  } else {
+    // upper_bound(indptr, pos) - 1
+    int64_t lo = 0, hi = p.n_rows;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (p.indptr[mid + 1] <= pos) lo = mid + 1; else hi = mid;
+    }
+    d = lo; s = p.indices[pos]; e = p.eids ? p.eids[pos] : pos;
+  }
+  int64_t lk = 0, rk = 0, sl = 1, sr = 1;
+  for (int dd = p.b.ndim - 1; dd >= 0; --dd) {
+    const bool red_axis = (p.op == DGLB_OP_DOT && dd == p.b.ndim - 1);
+    const int64_t od = p.b.out[dd];
+    const int64_t i = rem % od;
+    rem /= od;
+    if (!red_axis) {
+      lk += (p.b.lhs[dd] == 1 ? 0 : i) * sl;
+      rk += (p.b.rhs[dd] == 1 ? 0 : i) * sr;
+    }
+    sl *= p.b.lhs[dd];
+    sr *= p.b.rhs[dd];
+  }
+  const int64_t lid = p.lhs_target == DGLB_TARGET_U ? s : (p.lhs_target == DGLB_TARGET_E ? e : d);
+  const int64_t rid = p.rhs_target == DGLB_TARGET_U ? s : (p.rhs_target == DGLB_TARGET_E ? e : d);
+  const float* l = p.L ? p.L + lid * p.b.lhs_len + lk : nullptr;
+  const float* r = p.R ? p.R + rid * p.b.rhs_len + rk : nullptr;
+  float val;
+  if (p.op == DGLB_OP_DOT) {
+    val = 0.f;
+    for (int64_t i = 0; i < p.reduce_size; ++i) val = __fadd_rn(val, __fmul_rn(__ldg(l + i), __ldg(r + i)));
+  } else {
+    const float lv = (p.op != DGLB_OP_COPY_RHS) ? __ldg(l) : 0.f;
+    const float rv = (p.op != DGLB_OP_COPY_LHS) ? __ldg(r) : 0.f;
+    switch (p.op) {
+      case DGLB_OP_ADD: val = __fadd_rn(lv, rv); break;
+      case DGLB_OP_SUB: val = __fsub_rn(lv, rv); break;
+      case DGLB_OP_MUL: val = __fmul_rn(lv, rv); break;
+      case DGLB_OP_DIV: val = __fdiv_rn(lv, rv); break;
+      case DGLB_OP_COPY_LHS: val = lv; break;
+      default: val = rv; break;
+    }
+  }
+  p.out[e * OL + (idx - pos * OL)] = val;
+}
+
+int sddmm_generic_f32(const GenericSddmmParams& g, cudaStream_t stream) {
+  const int64_t total = g.nnz * g.b.out_len;
+  const int64_t blocks = (total + kBlockThreads - 1) / kBlockThreads;
+  if (blocks == 0) return DGLB_OK;
+  if (blocks > 0x7fffffffLL) { set_error("sddmm generic: problem too large"); return DGLB_E_UNSUPPORTED; }
+  sddmm_generic_kernel<<<(unsigned)blocks, kBlockThreads, 0, stream>>>(g);
+  DGLB_LAUNCH_CHECK("sddmm_generic_kernel");
+  return DGLB_OK;
+}
+
+// ------------------------------------------------------------------ dispatch
+template <int VEC, int CH>
+static int launch_dot(const SddmmParams& p, int n_hub, cudaStream_t stream) {
+  const int rows_per_block = kBlockThreads / p.G;
+  const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
+  if (blocks > 0) {
+    sddmm_dot_kernel<VEC, CH, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+    DGLB_LAUNCH_CHECK("sddmm_dot_kernel");
+  }
+  if (n_hub > 0) {
+    sddmm_dot_kernel<VEC, CH, true><<<n_hub, kBlockThreads, 0, stream>>>(p);
+    DGLB_LAUNCH_CHECK("sddmm_dot_kernel(hub)");
+  }
+  return DGLB_OK;
+}
+
+template <int VEC, int CH, int OP>
+static int launch_ew(const SddmmParams& p, int n_hub, cudaStream_t stream) {
+  const int rows_per_block = kBlockThreads / p.G;
+  const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
+  if (blocks > 0) {
+    sddmm_ew_kernel<VEC, CH, OP, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+    DGLB_LAUNCH_CHECK("sddmm_ew_kernel");
+  }
+  if (n_hub > 0) {
+    sddmm_ew_kernel<VEC, CH, OP, true><<<n_hub, kBlockThreads, 0, stream>>>(p);
+    DGLB_LAUNCH_CHECK("sddmm_ew_kernel(hub)");
+  }
+  return DGLB_OK;
+}
+
+template <int OP>
+static int dispatch_ew(const SddmmParams& p, int vec, int ch, int n_hub, cudaStream_t stream) {
+#define DGLB_CASE(V, C) if (vec == V && ch == C) return launch_ew<V, C, OP>(p, n_hub, stream);
+  DGLB_CASE(4, 1) DGLB_CASE(4, 2) DGLB_CASE(4, 4)
+  DGLB_CASE(2, 1) DGLB_CASE(2, 2) DGLB_CASE(2, 4)
+  DGLB_CASE(1, 1) DGLB_CASE(1, 2) DGLB_CASE(1, 4)
+#undef DGLB_CASE
+  return DGLB_E_UNSUPPORTED;
+}
+
+// returns DGLB_E_UNSUPPORTED (without setting an error) when the vector path does not apply
+int sddmm_csr_fast_f32(int op, int64_t n_dst, const int32_t* indptr, const int32_t* indices,
+                       const int32_t* eids, const float* Uf, const float* Vf, const BcastShape& b,
+                       int64_t reduce_size, float* out, const int32_t* hub_rows, int32_t n_hub,
+                       int32_t hub_threshold, cudaStream_t stream) {
+  if (b.lhs_len != b.rhs_len) return DGLB_E_UNSUPPORTED;
+  for (int d = 0; d < b.ndim; ++d)
+    if (b.lhs[d] != b.rhs[d]) return DGLB_E_UNSUPPORTED;
+  const int64_t D = b.lhs_len;
+  if (D <= 0 || D >= (1 << 30)) return DGLB_E_UNSUPPORTED;
+  SddmmParams p;
+  p.indptr = indptr; p.indices = indices; p.eids = eids; p.U = Uf; p.V = Vf; p.out = out;
+  p.hub_rows = hub_rows; p.n_rows = n_dst; p.D = (int)D;
+  p.hub_threshold = (n_hub > 0 && hub_rows) ? hub_threshold : INT32_MAX;
+  if (!(n_hub > 0 && hub_rows)) n_hub = 0;
+  int vec = 4;
+  if (op != DGLB_OP_COPY_RHS) vec = min_int(vec, pick_vec(D, Uf));
+  if (op != DGLB_OP_COPY_LHS) vec = min_int(vec, pick_vec(D, Vf));
+  if (op == DGLB_OP_DOT) {
+    const int64_t H = b.out_len;
+    if (H > 1) {
+      // each head must be a power-of-two lane segment inside a single chunk
+      while (vec > 1 && (reduce_size % vec)) vec >>= 1;
+      const int64_t seg = reduce_size / vec;
+      if ((seg & (seg - 1)) != 0 || seg * H > 32) return DGLB_E_UNSUPPORTED;
+      int64_t cols = seg * H;
+      if ((cols & (cols - 1)) != 0 && group_lanes(cols) < cols) return DGLB_E_UNSUPPORTED;
+      p.seg = (int)seg;
+    }
+    p.H = (int)H;
+  } else {
+    vec = min_int(vec, pick_vec(D, out));
+  }
+  p.ncols = (int)(D / vec);
+  p.G = group_lanes(p.ncols);
+  p.log2G = 0;
+  while ((1 << p.log2G) < p.G) ++p.log2G;
+  if (op == DGLB_OP_DOT && p.H == 1) p.seg = p.G;
+  const int per_lane = (p.ncols + p.G - 1) / p.G;
+  const int ch = per_lane >= 4 ? 4 : (per_lane >= 2 ? 2 : 1);
+  if (op == DGLB_OP_DOT) {
+    if (p.H > 1 && ch != 1) return DGLB_E_UNSUPPORTED;
+#define DGLB_CASE(V, C) if (vec == V && ch == C) return launch_dot<V, C>(p, n_hub, stream);
+    DGLB_CASE(4, 1) DGLB_CASE(4, 2) DGLB_CASE(4, 4)
+    DGLB_CASE(2, 1) DGLB_CASE(2, 2) DGLB_CASE(2, 4)
+    DGLB_CASE(1, 1) DGLB_CASE(1, 2) DGLB_CASE(1, 4)
+#undef DGLB_CASE
+    return DGLB_E_UNSUPPORTED;
+  }
+  switch (op) {
+    case DGLB_OP_ADD: return dispatch_ew<DGLB_OP_ADD>(p, vec, ch, n_hub, stream);
+    case DGLB_OP_SUB: return dispatch_ew<DGLB_OP_SUB>(p, vec, ch, n_hub, stream);
+    case DGLB_OP_MUL: return dispatch_ew<DGLB_OP_MUL>(p, vec, ch, n_hub, stream);
+    case DGLB_OP_DIV: return dispatch_ew<DGLB_OP_DIV>(p, vec, ch, n_hub, stream);
+    case DGLB_OP_COPY_LHS: return dispatch_ew<DGLB_OP_COPY_LHS>(p, vec, ch, n_hub, stream);
+    case DGLB_OP_COPY_RHS: return dispatch_ew<DGLB_OP_COPY_RHS>(p, vec, ch, n_hub, stream);
+    default: return DGLB_E_UNSUPPORTED;
+  }
+}
+
+}  // namespace dglb

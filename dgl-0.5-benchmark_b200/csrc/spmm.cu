@@ -1,0 +1,454 @@
+// spmm.cu -- generalized SpMM on a CSR-like structure (the CSC of the graph for forward
+// aggregation, its CSR for the reverse graph), hand-written for sm_100a.
+//
+// Replaces upstream DGL v0.6.1 src/array/cuda/spmm.cu(h) (SpMMCsrKernel: one thread per
+// (row, feature), scalar loads, no balancing; CusparseCsrmm2 for copy_lhs/sum) behind
+// `_CAPI_DGLKernelSpMM`; reached from kernel/dgl-new.py:20 and every update_all() in
+// end_to_end/full_graph (e.g. main_dgl_citation_sage.py:75-77).
+//
+// Design (HBM-bound gather; no tensor cores -- ~0.25 flop/byte):
+//   * row-per-group: a power-of-two group of G<=32 lanes owns one destination row; each lane
+//     owns CH vector columns (VEC = 4/2/1 floats => LDG.128/64/32) spaced G apart, so a
+//     neighbour row is fetched by fully coalesced 16*G-byte requests.  G shrinks with the
+//     feature width so narrow features pack several rows into one warp.
+//   * the group's lanes fetch G column indices with ONE coalesced load and broadcast them with
+//     warp shuffles; U neighbour rows x CH chunks are issued back to back before the first
+//     add (U*CH = 8 independent 128-bit loads in flight per lane).
+//   * per output element the neighbours are accumulated strictly in CSR order with
+//     non-contracted fp32 ops, which reproduces the sequential order of DGL's CPU kernel
+//     (SpMMSumCsr) bit for bit, and makes the max/min arg tie-break (first wins) exact.
+//   * hub rows (nnz > threshold, listed by dglb_csr_find_hub_rows) are skipped by the row
+//     kernel and handled by a second kernel: one CTA per hub row, its groups take contiguous
+//     slices of the row, partials meet in shared memory and are combined in slice order
+//     (deterministic, no atomics; ties still resolve to the first CSR entry).
+//   * wide rows are processed in feature tiles of G*CH*VEC floats (indices re-read from L1).
+//   * anything that does not fit the vector paths (exotic broadcasts, add/sub/div with
+//     max/min) goes to a generic thread-per-(row,feature) kernel -- still CUDA, never CPU.
+#include "kernels.cuh"
+
+namespace dglb {
+
+enum : int { RMODE_NONE = 0, RMODE_FULL = 1, RMODE_HEAD = 2 };
+
+struct SpmmParams {
+  const int32_t* __restrict__ indptr;
+  const int32_t* __restrict__ indices;
+  const int32_t* __restrict__ eids;  // null => edge id == CSR position
+  const float* __restrict__ X;       // lhs rows (D floats each)
+  const float* __restrict__ W;       // rhs rows (rhs_len floats each)
+  float* __restrict__ out;
+  int32_t* __restrict__ arg_u;
+  int32_t* __restrict__ arg_e;
+  const float* __restrict__ row_scale;
+  const int32_t* __restrict__ hub_rows;
+  int64_t n_rows;
+  int D;        // out_len
+  int rhs_len;  // floats per rhs row
+  int inner;    // RMODE_HEAD: rhs column = k / inner
+  int ncols;    // D / VEC
+  int G, log2G;
+  int hub_threshold;
+};
+
+template <int VEC, int CH, int RED>
+struct Acc {
+  float a[CH][VEC];
+  int32_t au[RED == DGLB_REDUCE_SUM ? 1 : CH][RED == DGLB_REDUCE_SUM ? 1 : VEC];
+  int32_t ae[RED == DGLB_REDUCE_SUM ? 1 : CH][RED == DGLB_REDUCE_SUM ? 1 : VEC];
+  __device__ __forceinline__ void init() {
+    const float z = RED == DGLB_REDUCE_SUM ? 0.f : (RED == DGLB_REDUCE_MAX ? -INFINITY : INFINITY);
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        a[c][v] = z;
+        if constexpr (RED != DGLB_REDUCE_SUM) { au[c][v] = 0; ae[c][v] = 0; }
+      }
+  }
+};
+
+template <int RED>
+__device__ __forceinline__ void combine(float& acc, int32_t& au, int32_t& ae, float val, int32_t c,
+                                        int32_t e) {
+  if constexpr (RED == DGLB_REDUCE_SUM) {
+    acc = __fadd_rn(acc, val);
+  } else if constexpr (RED == DGLB_REDUCE_MAX) {
+    if (acc < val) { acc = val; au = c; ae = e; }
+  } else {
+    if (acc > val) { acc = val; au = c; ae = e; }
+  }
+}
+
+// Accumulate CSR positions [j0, j0+n) into `acc` for the feature tile starting at vector column
+// `tile0`.  n is uniform within the group, nmax is the warp-wide maximum of n so every lane of
+// the warp runs the same trip count (shuffles stay converged; extra trips are predicated off).
+template <int VEC, int CH, int OP, int RED, int RMODE>
+__device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0, int n, int nmax,
+                                                 int lg, int tile0, Acc<VEC, CH, RED>& acc) {
+  constexpr int U = 8 / CH;
+  constexpr bool USE_L = OP != DGLB_OP_COPY_RHS;
+  constexpr bool USE_R = OP != DGLB_OP_COPY_LHS;
+  constexpr bool NEED_E = USE_R || RED != DGLB_REDUCE_SUM;
+  const int G = p.G;
+  bool colv[CH];
+  int k[CH], hk[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int vc = tile0 + c * G + lg;
+    colv[c] = vc < p.ncols;
+    k[c] = vc * VEC;
+    hk[c] = (RMODE == RMODE_HEAD) ? k[c] / p.inner : 0;
+  }
+  for (int off = 0; off < nmax; off += G) {
+    const int m = min(max(n - off, 0), G);
+    int my_c = 0, my_e = 0;
+    if (lg < m) {
+      const int64_t j = j0 + off + lg;
+      if (USE_L || RED != DGLB_REDUCE_SUM) my_c = __ldg(p.indices + j);
+      if (NEED_E) my_e = p.eids ? __ldg(p.eids + j) : (int)j;
+    }
+    const int mmax = min(G, nmax - off);
+    for (int t = 0; t < mmax; t += U) {
+      int cc[U], ee[U];
+      FVec<VEC> xv[U][CH];
+      FVec<VEC> wv[U][CH];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        cc[u] = __shfl_sync(FULL_MASK, my_c, t + u, G);
+        ee[u] = NEED_E ? __shfl_sync(FULL_MASK, my_e, t + u, G) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool valid = (t + u) < m;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          if (valid && colv[c]) {
+            if constexpr (USE_L) xv[u][c] = ldg_vec<VEC>(p.X + (int64_t)cc[u] * p.D + k[c]);
+            if constexpr (RMODE == RMODE_FULL)
+              wv[u][c] = ldg_vec<VEC>(p.W + (int64_t)ee[u] * p.D + k[c]);
+            if constexpr (RMODE == RMODE_HEAD)
+              wv[u][c].v[0] = __ldg(p.W + (int64_t)ee[u] * p.rhs_len + hk[c]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool valid = (t + u) < m;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          if (valid && colv[c]) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              float val;
+              const float w = (RMODE == RMODE_HEAD) ? wv[u][c].v[0] : (USE_R ? wv[u][c].v[v] : 0.f);
+              if constexpr (OP == DGLB_OP_COPY_LHS) val = xv[u][c].v[v];
+              else if constexpr (OP == DGLB_OP_COPY_RHS) val = w;
+              else if constexpr (OP == DGLB_OP_MUL) val = __fmul_rn(xv[u][c].v[v], w);
+              else val = __fadd_rn(xv[u][c].v[v], w);
+              if constexpr (RED == DGLB_REDUCE_SUM) {
+                acc.a[c][v] = __fadd_rn(acc.a[c][v], val);
+              } else {
+                combine<RED>(acc.a[c][v], acc.au[c][v], acc.ae[c][v], val, cc[u], ee[u]);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ row-per-group kernel
+template <int VEC, int CH, int OP, int RED, int RMODE>
+__global__ void __launch_bounds__(kBlockThreads)
+spmm_rows_kernel(const SpmmParams p) {
+  const int G = p.G;
+  const int lg = threadIdx.x & (G - 1);
+  const int64_t row = ((int64_t)blockIdx.x * kBlockThreads + threadIdx.x) >> p.log2G;
+  int row_start = 0, deg = 0;
+  bool active = row < p.n_rows;
+  if (active) {
+    row_start = __ldg(p.indptr + row);
+    deg = __ldg(p.indptr + row + 1) - row_start;
+    if (deg > p.hub_threshold) { active = false; deg = 0; }  // left to the hub kernel
+  }
+  const int nmax = __reduce_max_sync(FULL_MASK, deg);
+  float scale = 1.f;
+  if (p.row_scale && active) scale = __ldg(p.row_scale + row);
+  for (int tile0 = 0; tile0 < p.ncols; tile0 += G * CH) {
+    Acc<VEC, CH, RED> acc;
+    acc.init();
+    accumulate_range<VEC, CH, OP, RED, RMODE>(p, row_start, deg, nmax, lg, tile0, acc);
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int vc = tile0 + c * G + lg;
+        if (vc < p.ncols) {
+          FVec<VEC> o;
+#pragma unroll
+          for (int v = 0; v < VEC; ++v)
+            o.v[v] = p.row_scale ? __fdiv_rn(acc.a[c][v], scale) : acc.a[c][v];
+          const int64_t off = row * (int64_t)p.D + (int64_t)vc * VEC;
+          st_vec<VEC>(p.out + off, o);
+          if constexpr (RED != DGLB_REDUCE_SUM) {
+            if (p.arg_u) st_vec_i32<VEC>(p.arg_u + off, acc.au[c]);
+            if (p.arg_e) st_vec_i32<VEC>(p.arg_e + off, acc.ae[c]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ hub rows: one CTA per row
+template <int VEC, int CH, int OP, int RED, int RMODE>
+__global__ void __launch_bounds__(kBlockThreads)
+spmm_hub_kernel(const SpmmParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int G = p.G;
+  const int tile_elems = G * CH * VEC;
+  const int n_groups = kBlockThreads >> p.log2G;
+  float* s_val = reinterpret_cast<float*>(smem_raw);                   // [n_groups][tile_elems]
+  int32_t* s_au = reinterpret_cast<int32_t*>(s_val + n_groups * tile_elems);
+  int32_t* s_ae = s_au + n_groups * tile_elems;
+
+  const int64_t row = p.hub_rows[blockIdx.x];
+  const int lg = threadIdx.x & (G - 1);
+  const int gidx = threadIdx.x >> p.log2G;
+  const int row_start = __ldg(p.indptr + row);
+  const int deg = __ldg(p.indptr + row + 1) - row_start;
+  const int per = (deg + n_groups - 1) / n_groups;
+  const int my_begin = min(gidx * per, deg);
+  const int my_n = min(per, deg - my_begin);
+  const int nmax = __reduce_max_sync(FULL_MASK, my_n);
+  const float scale = p.row_scale ? __ldg(p.row_scale + row) : 1.f;
+
+  for (int tile0 = 0; tile0 < p.ncols; tile0 += G * CH) {
+    Acc<VEC, CH, RED> acc;
+    acc.init();
+    accumulate_range<VEC, CH, OP, RED, RMODE>(p, (int64_t)row_start + my_begin, my_n, nmax, lg, tile0,
+                                              acc);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int el = (c * G + lg) * VEC;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        s_val[gidx * tile_elems + el + v] = acc.a[c][v];
+        if constexpr (RED != DGLB_REDUCE_SUM) {
+          s_au[gidx * tile_elems + el + v] = acc.au[c][v];
+          s_ae[gidx * tile_elems + el + v] = acc.ae[c][v];
+        }
+      }
+    }
+    __syncthreads();
+    for (int el = threadIdx.x; el < tile_elems; el += kBlockThreads) {
+      const int kk = tile0 * VEC + el;
+      if (kk < p.D) {
+        float a = s_val[el];
+        int32_t au = 0, ae = 0;
+        if constexpr (RED != DGLB_REDUCE_SUM) { au = s_au[el]; ae = s_ae[el]; }
+        for (int g = 1; g < n_groups; ++g) {  // slice order == CSR order: first still wins ties
+          const float b = s_val[g * tile_elems + el];
+          if constexpr (RED == DGLB_REDUCE_SUM) {
+            a = __fadd_rn(a, b);
+          } else {
+            combine<RED>(a, au, ae, b, s_au[g * tile_elems + el], s_ae[g * tile_elems + el]);
+          }
+        }
+        const int64_t off = row * (int64_t)p.D + kk;
+        p.out[off] = p.row_scale ? __fdiv_rn(a, scale) : a;
+        if constexpr (RED != DGLB_REDUCE_SUM) {
+          if (p.arg_u) p.arg_u[off] = au;
+          if (p.arg_e) p.arg_e[off] = ae;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ generic fallback
+struct GenericSpmmParams {
+  const int32_t* indptr;
+  const int32_t* indices;
+  const int32_t* eids;
+  const float* X;
+  const float* W;
+  float* out;
+  int32_t* arg_u;
+  int32_t* arg_e;
+  const float* row_scale;
+  int64_t n_rows;
+  int op, red;
+  BcastShape b;
+};
+
+__device__ __forceinline__ float generic_binop(int op, float l, float r) {
+  switch (op) {
+    case DGLB_OP_ADD: return __fadd_rn(l, r);
+    case DGLB_OP_SUB: return __fsub_rn(l, r);
+    case DGLB_OP_MUL: return __fmul_rn(l, r);
+    case DGLB_OP_DIV: return __fdiv_rn(l, r);
+    case DGLB_OP_COPY_LHS: return l;
+    default: return r;
+  }
+}
+
+__global__ void __launch_bounds__(kBlockThreads) spmm_generic_kernel(const GenericSpmmParams p) {
+  const int64_t idx = (int64_t)blockIdx.x * kBlockThreads + threadIdx.x;
+  const int64_t D = p.b.out_len;
+  if (idx >= p.n_rows * D) return;
+  const int64_t row = idx / D;
+  int64_t rem = idx - row * D;
+  int64_t lk = 0, rk = 0, sl = 1, sr = 1;
+  for (int d = p.b.ndim - 1; d >= 0; --d) {
+    const int64_t i = rem % p.b.out[d];
+    rem /= p.b.out[d];
+    lk += (p.b.lhs[d] == 1 ? 0 : i) * sl;
+    rk += (p.b.rhs[d] == 1 ? 0 : i) * sr;
+    sl *= p.b.lhs[d];
+    sr *= p.b.rhs[d];
+  }
+  const bool use_l = p.op != DGLB_OP_COPY_RHS, use_r = p.op != DGLB_OP_COPY_LHS;
+  const int start = p.indptr[row], end = p.indptr[row + 1];
+  float acc = p.red == DGLB_REDUCE_SUM ? 0.f : (p.red == DGLB_REDUCE_MAX ? -INFINITY : INFINITY);
+  int32_t au = 0, ae = 0;
+  for (int j = start; j < end; ++j) {
+    const int32_t c = p.indices[j];
+    const int32_t e = p.eids ? p.eids[j] : j;
+    const float l = use_l ? __ldg(p.X + (int64_t)c * p.b.lhs_len + lk) : 0.f;
+    const float r = use_r ? __ldg(p.W + (int64_t)e * p.b.rhs_len + rk) : 0.f;
+    const float val = generic_binop(p.op, l, r);
+    if (p.red == DGLB_REDUCE_SUM) acc = __fadd_rn(acc, val);
+    else if (p.red == DGLB_REDUCE_MAX) { if (acc < val) { acc = val; au = c; ae = e; } }
+    else { if (acc > val) { acc = val; au = c; ae = e; } }
+  }
+  if (p.row_scale) acc = __fdiv_rn(acc, p.row_scale[row]);
+  p.out[idx] = acc;
+  if (p.red != DGLB_REDUCE_SUM) {
+    if (p.arg_u) p.arg_u[idx] = au;
+    if (p.arg_e) p.arg_e[idx] = ae;
+  }
+}
+
+// ------------------------------------------------------------------ dispatch
+template <int VEC, int CH, int OP, int RED, int RMODE>
+static int launch_fast(const SpmmParams& p, int n_hub, cudaStream_t stream) {
+  const int rows_per_block = kBlockThreads / p.G;
+  const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
+  if (blocks > 0) {
+    spmm_rows_kernel<VEC, CH, OP, RED, RMODE><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+    DGLB_LAUNCH_CHECK("spmm_rows_kernel");
+  }
+  if (n_hub > 0) {
+    const size_t smem = (size_t)kBlockThreads * CH * VEC * 4 * (RED == DGLB_REDUCE_SUM ? 1 : 3);
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+      DGLB_CUDA(cudaFuncSetAttribute(spmm_hub_kernel<VEC, CH, OP, RED, RMODE>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    spmm_hub_kernel<VEC, CH, OP, RED, RMODE><<<n_hub, kBlockThreads, smem, stream>>>(p);
+    DGLB_LAUNCH_CHECK("spmm_hub_kernel");
+  }
+  return DGLB_OK;
+}
+
+template <int OP, int RED, int RMODE>
+static int dispatch_vec_ch(SpmmParams& p, int vec, int n_hub, cudaStream_t stream) {
+  p.ncols = p.D / vec;
+  p.G = group_lanes(p.ncols);
+  p.log2G = 0;
+  while ((1 << p.log2G) < p.G) ++p.log2G;
+  const int per_lane = (p.ncols + p.G - 1) / p.G;
+  const int ch = per_lane >= 4 ? 4 : (per_lane >= 2 ? 2 : 1);
+#define DGLB_CASE(V, C) \
+  if (vec == V && ch == C) return launch_fast<V, C, OP, RED, RMODE>(p, n_hub, stream);
+  DGLB_CASE(4, 1) DGLB_CASE(4, 2) DGLB_CASE(4, 4)
+  DGLB_CASE(2, 1) DGLB_CASE(2, 2) DGLB_CASE(2, 4)
+  DGLB_CASE(1, 1) DGLB_CASE(1, 2) DGLB_CASE(1, 4)
+#undef DGLB_CASE
+  set_error("spmm: no kernel for vec=%d ch=%d", vec, ch);
+  return DGLB_E_UNSUPPORTED;
+}
+
+template <int OP, int RMODE>
+static int dispatch_red(SpmmParams& p, int red, int vec, int n_hub, cudaStream_t stream) {
+  switch (red) {
+    case DGLB_REDUCE_SUM: return dispatch_vec_ch<OP, DGLB_REDUCE_SUM, RMODE>(p, vec, n_hub, stream);
+    case DGLB_REDUCE_MAX: return dispatch_vec_ch<OP, DGLB_REDUCE_MAX, RMODE>(p, vec, n_hub, stream);
+    default: return dispatch_vec_ch<OP, DGLB_REDUCE_MIN, RMODE>(p, vec, n_hub, stream);
+  }
+}
+
+static int and_vec(int a, int b) { return a < b ? a : b; }
+
+int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                 const int32_t* indptr, const int32_t* indices, const int32_t* eids, const float* X,
+                 const float* W, const BcastShape& b, float* out, int32_t* arg_u, int32_t* arg_e,
+                 const float* row_scale, const int32_t* hub_rows, int32_t n_hub,
+                 int32_t hub_threshold, cudaStream_t stream) {
+  (void)n_cols;
+  (void)nnz;
+  if (n_rows == 0 || b.out_len == 0) return DGLB_OK;
+  const bool use_l = op != DGLB_OP_COPY_RHS, use_r = op != DGLB_OP_COPY_LHS;
+  // ---- classify the broadcast pattern
+  int rmode = -1;
+  int64_t inner = 1;
+  if (op == DGLB_OP_COPY_LHS) {
+    rmode = RMODE_NONE;
+  } else if (op == DGLB_OP_COPY_RHS) {
+    rmode = RMODE_FULL;
+  } else if (b.lhs_len == b.out_len) {
+    if (b.rhs_len == b.out_len) {
+      rmode = RMODE_FULL;
+    } else {
+      // rhs equals lhs on the leading dims and is 1 on the trailing ones => column = k / inner
+      int t = b.ndim;
+      while (t > 0 && b.rhs[t - 1] == 1) --t;
+      bool ok = true;
+      for (int d = 0; d < t; ++d) ok = ok && (b.rhs[d] == b.lhs[d]);
+      if (ok) {
+        for (int d = t; d < b.ndim; ++d) inner *= b.lhs[d];
+        rmode = RMODE_HEAD;
+      }
+    }
+  }
+  const bool fast_op = (op == DGLB_OP_COPY_LHS || op == DGLB_OP_COPY_RHS ||
+                        (op == DGLB_OP_MUL && reduce == DGLB_REDUCE_SUM));
+  if (rmode >= 0 && fast_op && b.out_len < (1 << 30)) {
+    SpmmParams p;
+    p.indptr = indptr; p.indices = indices; p.eids = eids;
+    p.X = X; p.W = W; p.out = out; p.arg_u = arg_u; p.arg_e = arg_e;
+    p.row_scale = row_scale; p.hub_rows = hub_rows;
+    p.n_rows = n_rows; p.D = (int)b.out_len; p.rhs_len = (int)b.rhs_len; p.inner = (int)inner;
+    p.hub_threshold = (n_hub > 0 && hub_rows) ? hub_threshold : INT32_MAX;
+    if (!(n_hub > 0 && hub_rows)) n_hub = 0;
+    int vec = pick_vec(b.out_len, out);
+    if (use_l) vec = and_vec(vec, pick_vec(b.out_len, X));
+    if (rmode == RMODE_FULL) vec = and_vec(vec, pick_vec(b.out_len, W));
+    if (rmode == RMODE_HEAD) { while (inner % vec) vec >>= 1; }
+    if (reduce != DGLB_REDUCE_SUM) {
+      if (arg_u) vec = and_vec(vec, pick_vec(b.out_len, arg_u));
+      if (arg_e) vec = and_vec(vec, pick_vec(b.out_len, arg_e));
+    }
+    if (op == DGLB_OP_COPY_LHS) return dispatch_red<DGLB_OP_COPY_LHS, RMODE_NONE>(p, reduce, vec, n_hub, stream);
+    if (op == DGLB_OP_COPY_RHS) return dispatch_red<DGLB_OP_COPY_RHS, RMODE_FULL>(p, reduce, vec, n_hub, stream);
+    if (rmode == RMODE_FULL) return dispatch_vec_ch<DGLB_OP_MUL, DGLB_REDUCE_SUM, RMODE_FULL>(p, vec, n_hub, stream);
+    return dispatch_vec_ch<DGLB_OP_MUL, DGLB_REDUCE_SUM, RMODE_HEAD>(p, vec, n_hub, stream);
+  }
+  // ---- generic path
+  GenericSpmmParams g;
+  g.indptr = indptr; g.indices = indices; g.eids = eids; g.X = X; g.W = W; g.out = out;
+  g.arg_u = arg_u; g.arg_e = arg_e; g.row_scale = row_scale; g.n_rows = n_rows;
+  g.op = op; g.red = reduce; g.b = b;
+  (void)use_r;
+  const int64_t total = n_rows * b.out_len;
+  const int64_t blocks = (total + kBlockThreads - 1) / kBlockThreads;
+  if (blocks > 0x7fffffffLL) { set_error("spmm generic: problem too large"); return DGLB_E_UNSUPPORTED; }
+  spmm_generic_kernel<<<(unsigned)blocks, kBlockThreads, 0, stream>>>(g);
+  DGLB_LAUNCH_CHECK("spmm_generic_kernel");
+  return DGLB_OK;
+}
+
+}  // namespace dglb

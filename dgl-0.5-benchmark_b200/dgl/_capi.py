@@ -1,0 +1,127 @@
+"""ctypes binding of the C-ABI in include/dglb200.h (lib/libdglb200.so).
+
+This is the only door from Python into the sm_100a kernels.  There is NO CPU or PyTorch
+fallback behind it: if the shared library is missing, or an op is asked to run on tensors that
+are not on a CUDA device, the call raises.  torch is used for device memory and streams only.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdglb200.so")
+
+OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "copy_lhs": 4, "copy_rhs": 5, "dot": 6}
+REDUCERS = {"sum": 0, "max": 1, "min": 2}
+TARGETS = {"u": 0, "e": 1, "v": 2}
+F32 = 0
+
+_lib = None
+_launches = 0  # number of C-ABI compute calls issued (bench.py reports kernel launches from this)
+
+
+class DGLError(RuntimeError):
+    """Mirrors dgl.DGLError (upstream dgl._ffi.base.DGLError)."""
+
+
+_vp, _i64, _i32, _int, _f32, _u64 = (ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int,
+                                     ctypes.c_float, ctypes.c_uint64)
+_shape_t = ctypes.POINTER(ctypes.c_int64)
+
+_SIGNATURES = {
+    "dglb_abi_version": (_int, []),
+    "dglb_last_error": (ctypes.c_char_p, []),
+    "dglb_device_info": (_int, [ctypes.POINTER(_int)] * 3 + [ctypes.POINTER(_i64)]),
+    "dglb_set_device": (_int, [_int]),
+    "dglb_coo_to_csr_workspace_bytes": (ctypes.c_size_t, [_i64, _i64]),
+    "dglb_coo_to_csr": (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
+    "dglb_csr_degrees": (_int, [_i64, _vp, _vp, _vp]),
+    "dglb_is_identity_perm": (_int, [_i64, _vp, _vp, _vp]),
+    "dglb_csr_find_hub_rows": (_int, [_i64, _vp, _i32, _vp, _i64, _vp, _vp]),
+    "dglb_default_hub_threshold": (_i32, [_i64]),
+    "dglb_gspmm_csr": (_int, [_int, _int, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _shape_t,
+                              _shape_t, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "dglb_gsddmm_csr": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int,
+                               _shape_t, _shape_t, _vp, _vp, _i32, _i32, _vp]),
+    "dglb_gsddmm_coo": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _shape_t,
+                               _shape_t, _vp, _vp]),
+    "dglb_edge_softmax_fwd": (_int, [_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "dglb_edge_softmax_bwd": (_int, [_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "dglb_gat_fused_fwd": (_int, [_int, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _u64, _vp, _vp, _vp, _vp,
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "dglb_gat_fused_bwd_dst": (_int, [_int, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _u64, _vp, _vp, _vp,
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "dglb_gat_fused_bwd_src": (_int, [_int, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _u64, _vp, _vp, _vp,
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+}
+
+
+def exported_symbols():
+    """Every entry point include/dglb200.h declares (tests check the .so exports them all)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Load lib/libdglb200.so (built by dgl-0.5-benchmark_b200/build.py).  Fails loudly if absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DGLError(
+                "native library %s not found: build it with `python dgl-0.5-benchmark_b200/build.py` "
+                "(there is no CPU / PyTorch fallback for the sparse kernels)" % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        if l.dglb_abi_version() != 1:
+            raise DGLError("libdglb200.so ABI version mismatch")
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().dglb_last_error().decode("utf-8", "replace")
+        raise DGLError("%s failed (status %d): %s" % (what, rc, msg))
+
+
+def launches():
+    return _launches
+
+
+def count_launch(n=1):
+    global _launches
+    _launches += n
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def shape_arr(shape):
+    return (ctypes.c_int64 * len(shape))(*shape)
+
+
+def require_cuda(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise DGLError("dgl-b200 sparse kernels are CUDA-only (sm_100a); got a tensor on %s. "
+                           "There is no CPU fallback." % t.device)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise DGLError("expected all operands on one device, got %s and %s" % (dev, t.device))
+    return dev
+
+
+def enter(dev):
+    """Select the device in the library's CUDA runtime and return the current torch stream handle."""
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    check(lib().dglb_set_device(idx), "dglb_set_device")
+    return torch.cuda.current_stream(idx).cuda_stream

@@ -1,0 +1,186 @@
+"""Device-resident graph structure: COO + lazily materialised CSC / CSR with the edge-id permutation.
+
+Plays the role of upstream DGL v0.6.1 src/graph/unit_graph.cc (UnitGraph: COO/CSR/CSC holder with
+lazy, cached conversion; `Reverse` swaps CSR and CSC zero-copy) and python/dgl/heterograph_index.py
+for the single-node-type / single-edge-type graphs every in-scope script builds
+(kernel/utils.py:37-40 `dgl.graph(g.edges())`, main_dgl_citation_sage.py:190-191).
+
+Sparse formats follow SURVEY.md Appendix A.1: CSC = STABLE sort of the edges by destination
+(`data` = edge ids, increasing inside a row); CSR = the same by source.  When the COO is already
+sorted the permutation is the identity and is dropped (eids=None), which removes a 4-byte
+gather per edge from every kernel.
+"""
+import torch
+
+from . import _capi
+
+
+class CSRView:
+    """indptr / indices / eids (None == identity) over `n_rows` rows, all int32 device tensors,
+    plus per-threshold hub-row lists (caller-owned metadata of the C-ABI)."""
+
+    __slots__ = ("n_rows", "n_cols", "indptr", "indices", "eids", "_hubs", "_deg", "_deg_f")
+
+    def __init__(self, n_rows, n_cols, indptr, indices, eids):
+        self.n_rows, self.n_cols = n_rows, n_cols
+        self.indptr, self.indices, self.eids = indptr, indices, eids
+        self._hubs = {}
+        self._deg = None
+        self._deg_f = None
+
+    @property
+    def nnz(self):
+        return self.indices.shape[0]
+
+    def degrees(self):
+        if self._deg is None:
+            deg = torch.empty(self.n_rows, dtype=torch.int32, device=self.indptr.device)
+            if self.n_rows:
+                stream = _capi.enter(self.indptr.device)
+                _capi.check(_capi.lib().dglb_csr_degrees(self.n_rows, _capi.ptr(self.indptr), _capi.ptr(deg), stream),
+                            "dglb_csr_degrees")
+            self._deg = deg
+        return self._deg
+
+    def mean_divisor(self):
+        """float(clamp(deg, 1)) -- the divisor of reducer 'mean' (upstream ops/spmm.py)."""
+        if self._deg_f is None:
+            self._deg_f = self.degrees().clamp(min=1).to(torch.float32)
+        return self._deg_f
+
+    def hubs(self, threshold):
+        """(hub_rows tensor or None, n_hub) for rows with nnz > threshold; cached per threshold."""
+        hit = self._hubs.get(threshold)
+        if hit is None:
+            dev = self.indptr.device
+            n_hub_t = torch.zeros(1, dtype=torch.int32, device=dev)
+            cap = max(1, min(self.n_rows, self.nnz // max(threshold, 1) + 1))
+            rows = torch.empty(cap, dtype=torch.int32, device=dev)
+            stream = _capi.enter(dev)
+            _capi.check(_capi.lib().dglb_csr_find_hub_rows(self.n_rows, _capi.ptr(self.indptr), int(threshold),
+                                                           _capi.ptr(rows), cap, _capi.ptr(n_hub_t), stream),
+                        "dglb_csr_find_hub_rows")
+            n_hub = int(n_hub_t.item())  # one-off sync per (graph, threshold)
+            assert n_hub <= cap
+            hit = (rows[:n_hub].contiguous() if n_hub else None, n_hub)
+            self._hubs[threshold] = hit
+        return hit
+
+
+def build_csr(n_rows, n_cols, row, col):
+    """Stable sort of (row, col) by row on the device -> CSRView."""
+    dev = row.device
+    _capi.require_cuda(row, col)
+    nnz = row.shape[0]
+    indptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
+    indices = torch.empty(nnz, dtype=torch.int32, device=dev)
+    data = torch.empty(nnz, dtype=torch.int32, device=dev)
+    l = _capi.lib()
+    ws_bytes = l.dglb_coo_to_csr_workspace_bytes(n_rows, nnz)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    stream = _capi.enter(dev)
+    _capi.check(l.dglb_coo_to_csr(n_rows, nnz, _capi.ptr(row), _capi.ptr(col), _capi.ptr(indptr),
+                                  _capi.ptr(indices), _capi.ptr(data), _capi.ptr(ws), ws_bytes, stream),
+                "dglb_coo_to_csr")
+    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    _capi.check(l.dglb_is_identity_perm(nnz, _capi.ptr(data), _capi.ptr(flag), stream), "dglb_is_identity_perm")
+    identity = bool(flag.item())
+    return CSRView(n_rows, n_cols, indptr, indices, None if identity else data)
+
+
+class GraphIndex:
+    """One (src type, edge type, dst type) relation: n_src x n_dst, E edges in creation order."""
+
+    def __init__(self, src, dst, n_src, n_dst, idtype=None, _shared=None):
+        self.src, self.dst = src, dst  # edge-id order; int32 or int64 tensors (any device)
+        self.n_src, self.n_dst = int(n_src), int(n_dst)
+        self.idtype = idtype if idtype is not None else src.dtype
+        # caches shared with the reversed view
+        self._c = _shared if _shared is not None else {"csc": None, "csr": None, "coo32": None,
+                                                         "formats": {"coo", "csr", "csc"}}
+        self._rev = False
+
+    # ---- basic properties
+    @property
+    def device(self):
+        return self.src.device
+
+    @property
+    def n_edges(self):
+        return self.src.shape[0]
+
+    def reverse(self):
+        """Edge-direction reversal; CSC and CSR swap roles zero-copy (upstream UnitGraph::Reverse)."""
+        g = GraphIndex(self.dst, self.src, self.n_dst, self.n_src, self.idtype, _shared=self._c)
+        g._rev = not self._rev
+        return g
+
+    def astype(self, idtype):
+        if idtype == self.idtype:
+            return self
+        g = GraphIndex(self.src.to(idtype), self.dst.to(idtype), self.n_src, self.n_dst, idtype)
+        g._c["formats"] = set(self._c["formats"])
+        return g
+
+    def to(self, device):
+        device = torch.device(device)
+        if device == self.device:
+            return self
+        g = GraphIndex(self.src.to(device), self.dst.to(device), self.n_src, self.n_dst, self.idtype)
+        g._c["formats"] = set(self._c["formats"])
+        return g
+
+    def restrict_formats(self, formats):
+        g = GraphIndex(self.src, self.dst, self.n_src, self.n_dst, self.idtype)
+        g._c["formats"] = set(formats)
+        return g
+
+    def formats(self):
+        return set(self._c["formats"])
+
+    # ---- int32 COO for the kernels
+    def coo32(self):
+        key = "coo32"
+        if self._c[key] is None:
+            if self.n_src >= 2 ** 31 or self.n_dst >= 2 ** 31 or self.n_edges >= 2 ** 31:
+                raise _capi.DGLError("graph too large for int32 ids")
+            s = self.src if not self._rev else self.dst
+            d = self.dst if not self._rev else self.src
+            self._c[key] = (s.to(torch.int32).contiguous(), d.to(torch.int32).contiguous())
+        s, d = self._c[key]
+        return (s, d) if not self._rev else (d, s)
+
+    # ---- sparse formats (lazy, cached, shared with the reverse view)
+    def _fmt(self, which):
+        # `which` in the frame of THIS view; translate to the cache's (un-reversed) frame
+        key = which if not self._rev else ("csr" if which == "csc" else "csc")
+        if self._c[key] is None:
+            s, d = self._c["coo32"] if self._c["coo32"] is not None else (None, None)
+            if s is None:
+                self.coo32()
+                s, d = self._c["coo32"]
+            n_s = self.n_src if not self._rev else self.n_dst
+            n_d = self.n_dst if not self._rev else self.n_src
+            if key == "csc":
+                self._c[key] = build_csr(n_d, n_s, d, s)
+            else:
+                self._c[key] = build_csr(n_s, n_d, s, d)
+        return self._c[key]
+
+    def csc(self):
+        """rows = destination nodes, indices = source ids (the matrix SpMM traverses)."""
+        return self._fmt("csc")
+
+    def csr(self):
+        """rows = source nodes, indices = destination ids."""
+        return self._fmt("csr")
+
+    def in_degrees(self):
+        if self.device.type == "cuda":
+            return self.csc().degrees()
+        return torch.bincount(self.dst.long(), minlength=self.n_dst).to(torch.int32)
+
+    def out_degrees(self):
+        if self.device.type == "cuda":
+            return self.csr().degrees()
+        return torch.bincount(self.src.long(), minlength=self.n_src).to(torch.int32)

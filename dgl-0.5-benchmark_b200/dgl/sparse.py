@@ -1,0 +1,309 @@
+"""Kernel-level sparse ops: shape inference, output allocation and the C-ABI calls.
+
+Mirrors upstream DGL v0.6.1 python/dgl/sparse.py (`_gspmm`, `_gsddmm`, `infer_broadcast_shape`):
+same argument meaning (`op`, `reduce_op`, operands may be None, 1-D operands are treated as
+(n,1) and squeezed back), same error behaviour (DGLError on bad broadcast / missing operand),
+same "skip the kernel when the graph has no edges" rule.  Outputs are allocated by torch;
+everything else happens in lib/libdglb200.so on the current CUDA stream.
+"""
+import torch
+
+from . import _capi
+from ._capi import DGLError
+
+_TARGET = _capi.TARGETS
+
+
+def infer_broadcast_shape(op, shp1, shp2):
+    """Feature shape of op(lhs, rhs) under numpy-style broadcasting of the per-node / per-edge
+    feature shapes (leading node/edge dim excluded).  `dot` reduces the last dim to 1."""
+    pad1, pad2 = tuple(shp1), tuple(shp2)
+    if op == "copy_lhs":
+        return pad1
+    if op == "copy_rhs":
+        return pad2
+    if len(pad1) != len(pad2):
+        n = max(len(pad1), len(pad2))
+        pad1 = (1,) * (n - len(pad1)) + pad1
+        pad2 = (1,) * (n - len(pad2)) + pad2
+    for d1, d2 in zip(pad1, pad2):
+        if d1 != d2 and d1 != 1 and d2 != 1:
+            raise DGLError("Feature shapes {} and {} are not valid for broadcasting.".format(shp1, shp2))
+    rst = tuple(max(d1, d2) for d1, d2 in zip(pad1, pad2))
+    return rst[:-1] + (1,) if op == "dot" else rst
+
+
+def _shapes_for_abi(op, lhs, rhs):
+    """Right-aligned trailing shapes (>= 1 dim) handed to the C-ABI."""
+    ls = tuple(lhs.shape[1:]) if lhs is not None else None
+    rs = tuple(rhs.shape[1:]) if rhs is not None else None
+    if ls is None:
+        ls = rs
+    if rs is None:
+        rs = ls
+    n = max(len(ls), len(rs), 1)
+    ls = (1,) * (n - len(ls)) + ls
+    rs = (1,) * (n - len(rs)) + rs
+    if n > 5:
+        raise DGLError("feature tensors with more than 5 trailing dims are not supported")
+    return n, _capi.shape_arr(ls), _capi.shape_arr(rs)
+
+
+def _check_float32(*ts):
+    for t in ts:
+        if t is not None and t.dtype != torch.float32:
+            raise DGLError("dgl-b200 kernels compute in float32; got %s" % t.dtype)
+
+
+def _gspmm(gidx, op, reduce_op, u, e, row_scale=None):
+    """out[v] = reduce_{(s->v)} op(u[s], e[eid]).  Returns (out, (arg_u, arg_e)).
+
+    `gidx` is a GraphIndex; the kernel walks its CSC.  reduce_op in {sum, max, min}; `row_scale`
+    (float32, n_dst) fuses the mean divide.  arg_u / arg_e (graph idtype) only for max / min.
+    """
+    use_u = op != "copy_rhs"
+    use_e = op != "copy_lhs"
+    if use_u and u is None:
+        raise DGLError("gspmm: op %s needs node data" % op)
+    if use_e and e is None:
+        raise DGLError("gspmm: op %s needs edge data" % op)
+    if use_u and use_e and u.dtype != e.dtype:
+        raise DGLError("The node features' data type {} doesn't match edge features' data type {}, "
+                       "please convert them to the same type.".format(u.dtype, e.dtype))
+    if op not in ("add", "sub", "mul", "div", "copy_lhs", "copy_rhs"):
+        raise DGLError("gspmm: unknown op %s" % op)
+    if reduce_op not in ("sum", "max", "min"):
+        raise DGLError("gspmm: unknown reducer %s" % reduce_op)
+    u = u if use_u else None
+    e = e if use_e else None
+    _check_float32(u, e)
+    dev = _capi.require_cuda(u, e, gidx.src)
+    expand_u = expand_e = False
+    if use_u:
+        if u.shape[0] != gidx.n_src:
+            raise DGLError("gspmm: expect %d source-node rows, got %d" % (gidx.n_src, u.shape[0]))
+        if u.dim() == 1:
+            u, expand_u = u.unsqueeze(-1), True
+        u = u.contiguous()
+    if use_e:
+        if e.shape[0] != gidx.n_edges:
+            raise DGLError("gspmm: expect %d edge rows, got %d" % (gidx.n_edges, e.shape[0]))
+        if e.dim() == 1:
+            e, expand_e = e.unsqueeze(-1), True
+        e = e.contiguous()
+    feat_shape = infer_broadcast_shape(op, u.shape[1:] if use_u else (1,), e.shape[1:] if use_e else (1,))
+    ref = u if use_u else e
+    out_shape = (gidx.n_dst,) + tuple(feat_shape)
+    use_cmp = reduce_op in ("max", "min")
+    arg_u = arg_e = None
+    if gidx.n_edges == 0 or gidx.n_dst == 0:
+        v = torch.zeros(out_shape, dtype=ref.dtype, device=dev)
+        if use_cmp:
+            arg_u = torch.zeros(out_shape, dtype=gidx.idtype, device=dev) if use_u else None
+            arg_e = torch.zeros(out_shape, dtype=gidx.idtype, device=dev) if use_e else None
+    else:
+        csc = gidx.csc()
+        v = torch.empty(out_shape, dtype=ref.dtype, device=dev)  # the kernel writes every row
+        if use_cmp:
+            arg_u = torch.empty(out_shape, dtype=torch.int32, device=dev) if use_u else None
+            arg_e = torch.empty(out_shape, dtype=torch.int32, device=dev) if use_e else None
+        out_len = 1
+        for s in feat_shape:
+            out_len *= s
+        l = _capi.lib()
+        thr = l.dglb_default_hub_threshold(out_len)
+        hub_rows, n_hub = csc.hubs(thr)
+        ndim, ls, rs = _shapes_for_abi(op, u, e)
+        stream = _capi.enter(dev)
+        rc = l.dglb_gspmm_csr(_capi.OPS[op], _capi.REDUCERS[reduce_op], _capi.F32,
+                              csc.n_rows, csc.n_cols, csc.nnz,
+                              _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(csc.eids),
+                              _capi.ptr(u), _capi.ptr(e), ndim, ls, rs,
+                              _capi.ptr(v), _capi.ptr(arg_u), _capi.ptr(arg_e), _capi.ptr(row_scale),
+                              _capi.ptr(hub_rows), n_hub, thr, stream)
+        _capi.check(rc, "dglb_gspmm_csr")
+        _capi.count_launch(1 + (1 if n_hub else 0))
+        if use_cmp and gidx.idtype != torch.int32:
+            arg_u = arg_u.to(gidx.idtype) if arg_u is not None else None
+            arg_e = arg_e.to(gidx.idtype) if arg_e is not None else None
+    if (expand_u or not use_u) and (expand_e or not use_e):
+        v = v.squeeze(-1)
+        if arg_u is not None:
+            arg_u = arg_u.squeeze(-1)
+        if arg_e is not None:
+            arg_e = arg_e.squeeze(-1)
+    return v, (arg_u, arg_e)
+
+
+def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
+    """out[eid] = op(lhs[sel(lhs_target, eid)], rhs[sel(rhs_target, eid)]), edge-id order."""
+    if op not in ("add", "sub", "mul", "div", "dot", "copy_lhs", "copy_rhs"):
+        raise DGLError("gsddmm: unknown op %s" % op)
+    if lhs_target not in _TARGET or rhs_target not in _TARGET:
+        raise DGLError("gsddmm: targets must be one of u, e, v")
+    use_lhs = op != "copy_rhs"
+    use_rhs = op != "copy_lhs"
+    if use_lhs and lhs is None:
+        raise DGLError("gsddmm: op %s needs lhs data" % op)
+    if use_rhs and rhs is None:
+        raise DGLError("gsddmm: op %s needs rhs data" % op)
+    if use_lhs and use_rhs and lhs.dtype != rhs.dtype:
+        raise DGLError("The operands data type don't match: {} and {}, please convert them to the same "
+                       "type.".format(lhs.dtype, rhs.dtype))
+    lhs = lhs if use_lhs else None
+    rhs = rhs if use_rhs else None
+    _check_float32(lhs, rhs)
+    dev = _capi.require_cuda(lhs, rhs, gidx.src)
+    n_of = {"u": gidx.n_src, "e": gidx.n_edges, "v": gidx.n_dst}
+    expand_lhs = expand_rhs = False
+    if use_lhs:
+        if lhs.shape[0] != n_of[lhs_target]:
+            raise DGLError("gsddmm: lhs has %d rows, target '%s' has %d" % (lhs.shape[0], lhs_target, n_of[lhs_target]))
+        if lhs.dim() == 1:
+            lhs, expand_lhs = lhs.unsqueeze(-1), True
+        lhs = lhs.contiguous()
+    if use_rhs:
+        if rhs.shape[0] != n_of[rhs_target]:
+            raise DGLError("gsddmm: rhs has %d rows, target '%s' has %d" % (rhs.shape[0], rhs_target, n_of[rhs_target]))
+        if rhs.dim() == 1:
+            rhs, expand_rhs = rhs.unsqueeze(-1), True
+        rhs = rhs.contiguous()
+    feat_shape = infer_broadcast_shape(op, lhs.shape[1:] if use_lhs else (1,), rhs.shape[1:] if use_rhs else (1,))
+    ref = lhs if use_lhs else rhs
+    out = torch.empty((gidx.n_edges,) + tuple(feat_shape), dtype=ref.dtype, device=dev)
+    if gidx.n_edges > 0 and out.numel() > 0:
+        l = _capi.lib()
+        ndim, ls, rs = _shapes_for_abi(op, lhs, rhs)
+        stream = _capi.enter(dev)
+        lt, rt = _TARGET[lhs_target], _TARGET[rhs_target]
+        fmts = gidx.formats()
+        use_csr = ("csc" in fmts) and ((lhs_target == "u" and rhs_target == "v") or "coo" not in fmts)
+        if use_csr:
+            csc = gidx.csc()
+            width = 1
+            for s in ref.shape[1:]:
+                width *= s
+            thr = l.dglb_default_hub_threshold(width)
+            hub_rows, n_hub = csc.hubs(thr)
+            rc = l.dglb_gsddmm_csr(_capi.OPS[op], _capi.F32, lt, rt, csc.n_rows, csc.n_cols, csc.nnz,
+                                   _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(csc.eids),
+                                   _capi.ptr(lhs), _capi.ptr(rhs), ndim, ls, rs, _capi.ptr(out),
+                                   _capi.ptr(hub_rows), n_hub, thr, stream)
+            _capi.check(rc, "dglb_gsddmm_csr")
+            _capi.count_launch(1 + (1 if n_hub else 0))
+        else:
+            s32, d32 = gidx.coo32()
+            rc = l.dglb_gsddmm_coo(_capi.OPS[op], _capi.F32, lt, rt, gidx.n_src, gidx.n_dst, gidx.n_edges,
+                                   _capi.ptr(s32), _capi.ptr(d32), _capi.ptr(lhs), _capi.ptr(rhs), ndim, ls, rs,
+                                   _capi.ptr(out), stream)
+            _capi.check(rc, "dglb_gsddmm_coo")
+            _capi.count_launch(1)
+    if (expand_lhs or not use_lhs) and (expand_rhs or not use_rhs):
+        out = out.squeeze(-1)
+    return out
+
+
+def _edge_softmax_fwd(gidx, logits):
+    """softmax over each destination's in-edges; logits (E, ...) in edge-id order."""
+    _check_float32(logits)
+    dev = _capi.require_cuda(logits, gidx.src)
+    if logits.shape[0] != gidx.n_edges:
+        raise DGLError("edge_softmax: expect %d edge rows, got %d" % (gidx.n_edges, logits.shape[0]))
+    logits = logits.contiguous()
+    out = torch.empty_like(logits)
+    if gidx.n_edges == 0:
+        return out
+    heads = logits.numel() // gidx.n_edges
+    csc = gidx.csc()
+    l = _capi.lib()
+    thr = l.dglb_default_hub_threshold(max(heads, 64))
+    hub_rows, n_hub = csc.hubs(thr)
+    stream = _capi.enter(dev)
+    rc = l.dglb_edge_softmax_fwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(csc.eids),
+                                 _capi.ptr(logits), _capi.ptr(out), _capi.ptr(hub_rows), n_hub, thr, stream)
+    _capi.check(rc, "dglb_edge_softmax_fwd")
+    _capi.count_launch(1 + (1 if n_hub else 0))
+    return out
+
+
+def _edge_softmax_bwd(gidx, out, grad_out):
+    _check_float32(out, grad_out)
+    dev = _capi.require_cuda(out, grad_out, gidx.src)
+    out = out.contiguous()
+    grad_out = grad_out.contiguous()
+    grad = torch.empty_like(out)
+    if gidx.n_edges == 0:
+        return grad
+    heads = out.numel() // gidx.n_edges
+    csc = gidx.csc()
+    l = _capi.lib()
+    thr = l.dglb_default_hub_threshold(max(heads, 64))
+    hub_rows, n_hub = csc.hubs(thr)
+    stream = _capi.enter(dev)
+    rc = l.dglb_edge_softmax_bwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(csc.eids),
+                                 _capi.ptr(out), _capi.ptr(grad_out), _capi.ptr(grad), _capi.ptr(hub_rows), n_hub,
+                                 thr, stream)
+    _capi.check(rc, "dglb_edge_softmax_bwd")
+    _capi.count_launch(1 + (1 if n_hub else 0))
+    return grad
+
+
+def _gat_fwd(gidx, ft, el, er, slope, dropout_p, seed, want_scores=False):
+    """Fused GAT attention forward.  ft (n_src,H,F), el (n_src,H), er (n_dst,H) ->
+    rst (n_dst,H,F), row_max, row_sum (n_dst,H) [, scores (E,H)]."""
+    _check_float32(ft, el, er)
+    dev = _capi.require_cuda(ft, el, er, gidx.src)
+    ft, el, er = ft.contiguous(), el.contiguous(), er.contiguous()
+    H, F = ft.shape[1], ft.shape[2]
+    rst = torch.empty((gidx.n_dst, H, F), dtype=ft.dtype, device=dev)
+    row_max = torch.empty((gidx.n_dst, H), dtype=torch.float32, device=dev)
+    row_sum = torch.empty((gidx.n_dst, H), dtype=torch.float32, device=dev)
+    scores = torch.empty((gidx.n_edges, H), dtype=ft.dtype, device=dev) if want_scores else None
+    if gidx.n_dst == 0:
+        return rst, row_max, row_sum, scores
+    csc = gidx.csc()
+    l = _capi.lib()
+    thr = l.dglb_default_hub_threshold(H * F)
+    hub_rows, n_hub = csc.hubs(thr)
+    stream = _capi.enter(dev)
+    rc = l.dglb_gat_fused_fwd(_capi.F32, csc.n_rows, csc.n_cols, csc.nnz, H, F, float(slope), float(dropout_p),
+                              int(seed), _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(csc.eids),
+                              _capi.ptr(ft), _capi.ptr(el), _capi.ptr(er), _capi.ptr(rst), _capi.ptr(row_max),
+                              _capi.ptr(row_sum), _capi.ptr(scores), _capi.ptr(hub_rows), n_hub, thr, stream)
+    _capi.check(rc, "dglb_gat_fused_fwd")
+    _capi.count_launch(1 + (1 if n_hub else 0))
+    return rst, row_max, row_sum, scores
+
+
+def _gat_bwd(gidx, ft, el, er, row_max, row_sum, grad_rst, slope, dropout_p, seed):
+    """Fused GAT attention backward -> (grad_ft, grad_el, grad_er)."""
+    dev = _capi.require_cuda(ft, el, er, grad_rst, gidx.src)
+    grad_rst = grad_rst.contiguous()
+    H, F = ft.shape[1], ft.shape[2]
+    csc, csr = gidx.csc(), gidx.csr()
+    s1 = torch.empty((gidx.n_dst, H), dtype=torch.float32, device=dev)
+    grad_er = torch.empty((gidx.n_dst, H), dtype=ft.dtype, device=dev)
+    grad_ft = torch.empty_like(ft)
+    grad_el = torch.empty((gidx.n_src, H), dtype=ft.dtype, device=dev)
+    l = _capi.lib()
+    thr = l.dglb_default_hub_threshold(H * F)
+    stream = _capi.enter(dev)
+    if gidx.n_dst:
+        hub_rows, n_hub = csc.hubs(thr)
+        rc = l.dglb_gat_fused_bwd_dst(_capi.F32, csc.n_rows, csc.n_cols, csc.nnz, H, F, float(slope),
+                                      float(dropout_p), int(seed), _capi.ptr(csc.indptr), _capi.ptr(csc.indices),
+                                      _capi.ptr(csc.eids), _capi.ptr(ft), _capi.ptr(el), _capi.ptr(er),
+                                      _capi.ptr(row_max), _capi.ptr(row_sum), _capi.ptr(grad_rst), _capi.ptr(s1),
+                                      _capi.ptr(grad_er), _capi.ptr(hub_rows), n_hub, thr, stream)
+        _capi.check(rc, "dglb_gat_fused_bwd_dst")
+        _capi.count_launch(1 + (1 if n_hub else 0))
+    if gidx.n_src:
+        hub_rows, n_hub = csr.hubs(thr)
+        rc = l.dglb_gat_fused_bwd_src(_capi.F32, csr.n_rows, csr.n_cols, csr.nnz, H, F, float(slope),
+                                      float(dropout_p), int(seed), _capi.ptr(csr.indptr), _capi.ptr(csr.indices),
+                                      _capi.ptr(csr.eids), _capi.ptr(ft), _capi.ptr(el), _capi.ptr(er),
+                                      _capi.ptr(row_max), _capi.ptr(row_sum), _capi.ptr(s1), _capi.ptr(grad_rst),
+                                      _capi.ptr(grad_ft), _capi.ptr(grad_el), _capi.ptr(hub_rows), n_hub, thr, stream)
+        _capi.check(rc, "dglb_gat_fused_bwd_src")
+        _capi.count_launch(1 + (1 if n_hub else 0))
+    return grad_ft, grad_el, grad_er

@@ -1,0 +1,244 @@
+/*
+ * dglb200.h -- C-ABI of the B200-native sparse message-passing library.
+ *
+ * This is the drop-in boundary for the ONE hot path of dglai/dgl-0.5-benchmark:
+ * generalized SpMM / SDDMM / edge_softmax (+ fused GAT) as reached from
+ *   kernel/dgl-new.py:20   dgl.ops.gspmm(g, op, reduce, nfeat, efeat)
+ *   kernel/dgl-new.py:39   dgl.ops.gsddmm(g, op, ufeat, vfeat)
+ *   end_to_end/full_graph/node_classification/main_dgl_citation_sage.py:75-77 (update_all copy_src sum|mean)
+ *   end_to_end/full_graph/node_classification/main_dgl_arxiv_gat.py:9        (dgl.nn.pytorch.GATConv)
+ *
+ * The arithmetic behind those call sites lives in the un-vendored pip dependency
+ * DGL v0.6.1 (docker/build.dockerfile:14, README.md:6).  Each entry point below names
+ * the upstream packed function / kernel it replaces (paths are dmlc/dgl@0.6.1).
+ *
+ * Conventions
+ *   - plain C, no C++ / torch types; every pointer is a DEVICE pointer unless the
+ *     parameter name ends in `_host`.
+ *   - ids are int32 (every in-scope script calls g.int(): kernel/dgl-new.py:63,
+ *     main_dgl_citation_sage.py:191, main_dgl_product_sage.py:158); feature offsets are
+ *     computed in 64 bit (N*D and E*D exceed 2^31 at reddit/products scale).
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it, does
+ *     no hidden synchronisation and no allocation: the caller owns all buffers,
+ *     including workspaces whose size is returned by the matching *_workspace_bytes().
+ *   - return value: 0 = ok, negative = DGLB_E_* below; dglb_last_error() gives the
+ *     message for the calling thread.
+ *   - the library holds no per-graph state.  The only per-graph metadata is the
+ *     caller-owned "hub row" list (rows whose nnz exceeds a threshold) produced by
+ *     dglb_csr_find_hub_rows().
+ */
+#ifndef DGLB200_H_
+#define DGLB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGLB_ABI_VERSION 1
+
+/* status codes */
+#define DGLB_OK 0
+#define DGLB_E_INVALID (-1)     /* bad argument (shape mismatch, null pointer, unknown op) */
+#define DGLB_E_UNSUPPORTED (-2) /* combination not implemented on the device              */
+#define DGLB_E_CUDA (-3)        /* CUDA runtime error; message in dglb_last_error()       */
+#define DGLB_E_WORKSPACE (-4)   /* workspace too small                                    */
+
+/* binary ops: upstream src/array/kernel_decl.h / cpu/spmm_binary_ops.h (Add/Sub/Mul/Div/CopyLhs/CopyRhs/Dot) */
+#define DGLB_OP_ADD 0
+#define DGLB_OP_SUB 1
+#define DGLB_OP_MUL 2
+#define DGLB_OP_DIV 3
+#define DGLB_OP_COPY_LHS 4
+#define DGLB_OP_COPY_RHS 5
+#define DGLB_OP_DOT 6 /* gsddmm only */
+
+/* reducers: upstream cpu/spmm_binary_ops.h (Max/Min) and "sum".  "mean" is composed by the
+ * caller exactly like upstream python/dgl/ops/spmm.py (sum then divide by clamp(in_deg,1)),
+ * or fused through dglb_gspmm_csr's `row_scale` epilogue. */
+#define DGLB_REDUCE_SUM 0
+#define DGLB_REDUCE_MAX 1
+#define DGLB_REDUCE_MIN 2
+
+/* gsddmm operand targets: upstream python/dgl/sparse.py target_mapping {u:0, e:1, v:2} */
+#define DGLB_TARGET_U 0
+#define DGLB_TARGET_E 1
+#define DGLB_TARGET_V 2
+
+/* element types */
+#define DGLB_F32 0
+#define DGLB_BF16 1 /* storage bf16, fp32 accumulate (reserved; not all kernels) */
+
+#define DGLB_MAX_BCAST_NDIM 5
+
+/* ---------------------------------------------------------------- library / device info */
+
+int dglb_abi_version(void);
+/* message of the last failing call on this thread ("" if none) */
+const char* dglb_last_error(void);
+/* fills sm_count, compute capability, L2 bytes of the current device */
+int dglb_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes);
+/* make `device` current for the calling thread (the library links its own CUDA runtime) */
+int dglb_set_device(int device);
+
+/* ---------------------------------------------------------------- sparse format build
+ * replaces upstream src/array/cpu/spmat_op_impl_coo.cc::COOToCSR (order oracle) and
+ * src/array/cuda/coo2csr.cu / coo_sort.cu (device path).  Result is the STABLE sort of the
+ * edges by `row`: indptr[r+1]-indptr[r] = #edges with row r; within a row, entries appear in
+ * increasing edge id; indices[j] = col of that edge, data[j] = its edge id.
+ * To build the CSC used by SpMM pass row=dst, col=src; for the CSR (reverse graph) row=src.
+ */
+size_t dglb_coo_to_csr_workspace_bytes(int64_t n_rows, int64_t nnz);
+int dglb_coo_to_csr(int64_t n_rows, int64_t nnz,
+                    const int32_t* row, const int32_t* col,
+                    int32_t* indptr /* n_rows+1 */, int32_t* indices /* nnz */, int32_t* data /* nnz */,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* degrees = diff(indptr): upstream UnitGraph::InDegrees / OutDegrees */
+int dglb_csr_degrees(int64_t n_rows, const int32_t* indptr, int32_t* deg, void* stream);
+
+/* 1 if data[j]==j for all j (row-sorted COO fast path of COOToCSR), written to *flag (device int32) */
+int dglb_is_identity_perm(int64_t n, const int32_t* data, int32_t* flag, void* stream);
+
+/* hub rows: rows with nnz > threshold, in no particular order (every hub row is processed
+ * independently, so results do not depend on it).  *n_hub (device int32) receives the count,
+ * hub_rows (capacity `cap`) the ids (writes beyond cap are dropped, the count stays exact). */
+int dglb_csr_find_hub_rows(int64_t n_rows, const int32_t* indptr, int32_t threshold,
+                           int32_t* hub_rows, int64_t cap, int32_t* n_hub, void* stream);
+/* threshold the library recommends for a given feature width (elements) */
+int32_t dglb_default_hub_threshold(int64_t out_len);
+
+/* ---------------------------------------------------------------- generalized SpMM
+ * replaces upstream FFI `_CAPI_DGLKernelSpMM` (src/array/kernel.cc::SpMM ->
+ * cuda/spmm.cu::SpMMCsr / CusparseCsrmm2 / cuda/spmm.cuh::SpMMCsrKernel).
+ *
+ *   out[r, k] = REDUCE_{j in [indptr[r], indptr[r+1])}  op( ufeat[indices[j], lk], efeat[eid(j), rk] )
+ *   eid(j) = eids ? eids[j] : j ;  (lk, rk) follow numpy broadcasting of the trailing
+ *   shapes lhs_shape / rhs_shape (right-aligned, `ndim` entries each, host arrays; for
+ *   copy_lhs / copy_rhs pass the used operand's shape for both).
+ *
+ *  - sum: `out` is fully written (empty rows -> 0), callers need not zero it.
+ *  - max/min: strict compare in row order => the FIRST entry in CSR order wins ties;
+ *    arg_u[r,k] = indices[j*], arg_e[r,k] = eid(j*) (either may be NULL); empty rows ->
+ *    out = -/+inf, args = 0 (the Python layer replaces the infinities by 0, as upstream
+ *    python/dgl/ops/spmm.py does).
+ *  - row_scale (may be NULL): fused epilogue out[r,:] = out[r,:] / row_scale[r] (IEEE division),
+ *    used for reducer "mean" with row_scale = float(clamp(in_deg,1)).
+ *  - hub_rows/n_hub (may be NULL/0): rows listed there (nnz > hub_threshold) are processed by
+ *    the split-row path (one CTA per row) instead of the row-per-group path; the list must
+ *    come from dglb_csr_find_hub_rows(indptr, hub_threshold).
+ */
+int dglb_gspmm_csr(int op, int reduce, int dtype,
+                   int64_t n_rows, int64_t n_cols, int64_t nnz,
+                   const int32_t* indptr, const int32_t* indices, const int32_t* eids,
+                   const void* ufeat, const void* efeat,
+                   int ndim, const int64_t* lhs_shape_host, const int64_t* rhs_shape_host,
+                   void* out, int32_t* arg_u, int32_t* arg_e,
+                   const float* row_scale,
+                   const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
+                   void* stream);
+
+/* ---------------------------------------------------------------- generalized SDDMM
+ * replaces upstream FFI `_CAPI_DGLKernelSDDMM` (src/array/kernel.cc::SDDMM ->
+ * cuda/sddmm.cuh::SDDMMCooKernel / SDDMMCsrKernel).
+ *
+ *   out[e, k] = op( lhs[sel(lhs_target, e), lk], rhs[sel(rhs_target, e), rk] )      (edge-id order)
+ *   sel(U,e)=src[e], sel(E,e)=e, sel(V,e)=dst[e];  op DOT reduces the LAST dim (which must match
+ *   in both shapes) and the output's last dim becomes 1.
+ *
+ * Two traversals:
+ *   _csr : destination-major over the CSC (indptr over dst, indices = src, eids = edge id).
+ *          (U,V) targets with equal shapes take the vectorised path in which the dst row is read
+ *          once per row; everything else a generic kernel (row found by binary search).
+ *   _coo : edge-parallel over (src[e], dst[e]); any targets / broadcast.
+ */
+int dglb_gsddmm_csr(int op, int dtype, int lhs_target, int rhs_target,
+                    int64_t n_dst, int64_t n_src, int64_t nnz,
+                    const int32_t* indptr, const int32_t* indices, const int32_t* eids,
+                    const void* lhs, const void* rhs,
+                    int ndim, const int64_t* lhs_shape_host, const int64_t* rhs_shape_host,
+                    void* out,
+                    const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
+                    void* stream);
+
+int dglb_gsddmm_coo(int op, int dtype, int lhs_target, int rhs_target,
+                    int64_t n_src, int64_t n_dst, int64_t nnz,
+                    const int32_t* src, const int32_t* dst,
+                    const void* lhs, const void* rhs,
+                    int ndim, const int64_t* lhs_shape_host, const int64_t* rhs_shape_host,
+                    void* out, void* stream);
+
+/* ---------------------------------------------------------------- edge_softmax (norm_by='dst')
+ * replaces the 4+1 (fwd) / 2+2 (bwd) launch composite of upstream
+ * python/dgl/backend/pytorch/sparse.py::EdgeSoftmax with one kernel each.
+ *   fwd: out[e,h] = exp(logits[e,h] - max_v) / sum_v  over the in-edges of v = dst[e]
+ *   bwd: grad_logits[e,h] = out*g - out * sum_{in(v)} (out*g)
+ * logits/out/grad are (E, H) in edge-id order; indptr is the CSC over dst, eids its data.
+ */
+int dglb_edge_softmax_fwd(int dtype, int64_t n_dst, int64_t nnz, int64_t n_heads,
+                          const int32_t* indptr, const int32_t* eids,
+                          const void* logits, void* out,
+                          const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
+                          void* stream);
+int dglb_edge_softmax_bwd(int dtype, int64_t n_dst, int64_t nnz, int64_t n_heads,
+                          const int32_t* indptr, const int32_t* eids,
+                          const void* out, const void* grad_out, void* grad_logits,
+                          const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
+                          void* stream);
+
+/* ---------------------------------------------------------------- fused GAT attention
+ * replaces, for dgl.nn.pytorch.GATConv.forward (upstream python/dgl/nn/pytorch/conv/gatconv.py;
+ * written-out twin: main_pyg_arxiv_gat.py:98-111), the chain
+ *   apply_edges(u_add_v) -> leaky_relu -> edge_softmax -> attn_drop -> update_all(u_mul_e, sum)
+ * with ONE forward kernel that never writes a per-edge tensor:
+ *   e_j   = leaky_relu(el[src_j,h] + er[v,h], slope);  a_j = softmax_j(e)
+ *   rst[v,h,:] = sum_j a_j * drop_j * ft[src_j,h,:]
+ * and saves per-destination row_max[v,h], row_sum[v,h] for the backward.  drop_j is the
+ * attention-dropout factor (0 or 1/(1-p)) derived from a counter-based hash of
+ * (seed, edge id, head), so the backward regenerates it; dropout_p = 0 disables it.
+ * Backward is two kernels that recompute the scores (dd_j = drop_j * ft[src_j,h,:].grad_rst[v,h,:]):
+ *   _bwd_dst (CSC over dst): s1[v,h] = sum_j a_j*dd_j ; grad_er[v,h] = sum_j a_j*(dd_j - s1)*lrelu'_j
+ *   _bwd_src (CSR over src): grad_ft[u,h,:] = sum_{u->v} a*drop*grad_rst[v,h,:] ;
+ *                            grad_el[u,h]   = sum_{u->v} a*(dd - s1[v,h])*lrelu'
+ * optional `edge_scores` (E,H) in edge-id order receives a_j (before dropout); pass NULL on the
+ * training path.  n_heads <= 8.  hub lists refer to the matrix each kernel traverses.
+ */
+int dglb_gat_fused_fwd(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz,
+                       int64_t n_heads, int64_t head_dim, float negative_slope,
+                       float dropout_p, uint64_t seed,
+                       const int32_t* indptr, const int32_t* indices, const int32_t* eids,
+                       const void* ft, const void* el, const void* er,
+                       void* rst, float* row_max, float* row_sum,
+                       void* edge_scores,
+                       const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
+                       void* stream);
+
+int dglb_gat_fused_bwd_dst(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz,
+                           int64_t n_heads, int64_t head_dim, float negative_slope,
+                           float dropout_p, uint64_t seed,
+                           const int32_t* indptr, const int32_t* indices, const int32_t* eids,
+                           const void* ft, const void* el, const void* er,
+                           const float* row_max, const float* row_sum,
+                           const void* grad_rst,
+                           float* s1 /* (n_dst,H) */, void* grad_er /* (n_dst,H) */,
+                           const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
+                           void* stream);
+
+int dglb_gat_fused_bwd_src(int dtype, int64_t n_src, int64_t n_dst, int64_t nnz,
+                           int64_t n_heads, int64_t head_dim, float negative_slope,
+                           float dropout_p, uint64_t seed,
+                           const int32_t* indptr_csr, const int32_t* indices_csr /* dst ids */,
+                           const int32_t* eids_csr,
+                           const void* ft, const void* el, const void* er,
+                           const float* row_max, const float* row_sum, const float* s1,
+                           const void* grad_rst,
+                           void* grad_ft /* (n_src,H,F) */, void* grad_el /* (n_src,H) */,
+                           const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGLB200_H_ */

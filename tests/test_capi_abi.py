@@ -1,0 +1,68 @@
+"""The C-ABI library loads and exports every symbol include/dglb200.h declares, and the ctypes
+signatures in dgl/_capi.py have the same arity as the header (no compute calls: CPU-only test)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "dglb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    funcs = {}
+    for m in re.finditer(r"\b(?:int|size_t|int32_t|const char\*)\s+(dglb_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        funcs[name] = n
+    return funcs
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("dglb_build", os.path.join(ROOT, "dgl-0.5-benchmark_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build()
+
+
+def test_header_declares_the_expected_entry_points():
+    funcs = _header_functions()
+    for name in ("dglb_coo_to_csr", "dglb_gspmm_csr", "dglb_gsddmm_csr", "dglb_gsddmm_coo", "dglb_edge_softmax_fwd",
+                 "dglb_edge_softmax_bwd", "dglb_gat_fused_fwd", "dglb_gat_fused_bwd_dst", "dglb_gat_fused_bwd_src"):
+        assert name in funcs
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = ctypes.CDLL(built_lib)
+    for name in _header_functions():
+        assert hasattr(lib, name), "libdglb200.so does not export %s" % name
+    assert lib.dglb_abi_version() == 1
+
+
+def test_ctypes_signatures_match_header_arity(built_lib):
+    from dgl import _capi
+    funcs = _header_functions()
+    assert set(_capi.exported_symbols()) == set(funcs)
+    for name, (_, argtypes) in _capi._SIGNATURES.items():
+        assert len(argtypes) == funcs[name], (name, len(argtypes), funcs[name])
+    _capi.lib()  # binds every symbol with its argtypes
+
+
+def test_argument_errors_are_reported_without_a_gpu(built_lib):
+    from dgl import _capi
+    l = _capi.lib()
+    shp = _capi.shape_arr((4,))
+    # unknown op -> DGLB_E_INVALID before any CUDA call
+    rc = l.dglb_gspmm_csr(99, 0, 0, 1, 1, 0, None, None, None, None, None, 1, shp, shp, None, None, None, None,
+                          None, 0, 0, None)
+    assert rc == -1 and b"unknown op" in l.dglb_last_error()
+    bad = _capi.shape_arr((3,))
+    rc = l.dglb_gsddmm_coo(0, 0, 0, 2, 1, 1, 1, None, None, ctypes.c_void_p(8), ctypes.c_void_p(8), 1, shp, bad,
+                           ctypes.c_void_p(8), None)
+    assert rc == -1 and b"broadcast" in l.dglb_last_error()
+    assert l.dglb_default_hub_threshold(602) == 653
+    assert l.dglb_default_hub_threshold(1) == 8192

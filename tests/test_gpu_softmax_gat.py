@@ -1,0 +1,166 @@
+"""-m gpu parity: fused edge_softmax (fwd/bwd) and the fused GAT attention kernels vs the CPU
+oracle (upstream's composite restated) and an fp64 torch autograd restatement of the math written
+out in main_pyg_arxiv_gat.py:98-111.  Tolerance 1e-5 * sum|terms| (north_star) for sums; softmax
+outputs within 1e-5 relative."""
+import numpy as np
+import pytest
+import torch
+
+import dgl
+from conftest import assert_close_sumscaled
+from gpu_util import graphs, n, t
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("H", [1, 2, 3, 4, 8, 12, 40])
+@pytest.mark.parametrize("kind", ["uniform", "powerlaw"])
+def test_edge_softmax_forward_backward(oracle, cuda, H, kind):
+    ne = 60000 if kind == "powerlaw" else 4000
+    nn_ = 800 if kind == "powerlaw" else 300
+    og, g, src, dst = graphs(oracle, nn_, nn_, ne, seed=H, kind=kind)
+    rng = np.random.default_rng(H)
+    z = (3 * rng.standard_normal((ne, H, 1))).astype(np.float32)
+    want = oracle.edge_softmax(og, z)
+    zt = t(z).requires_grad_(True)
+    got = dgl.ops.edge_softmax(g, zt)
+    assert got.shape == (ne, H, 1)
+    np.testing.assert_allclose(n(got), want, rtol=1e-5, atol=1e-30)
+    gout = rng.standard_normal((ne, H, 1)).astype(np.float32)
+    got.backward(t(gout))
+    wantg = oracle.edge_softmax_backward(og, want, gout)
+    # terms: a*g and a*acc with acc = sum a*g  => scale by a*(|g| + sum_in a|g|)
+    acc = np.zeros((nn_, H, 1))
+    np.add.at(acc, dst, np.abs(want * gout).astype(np.float64))
+    scale = np.abs(want) * (np.abs(gout) + acc[dst])
+    assert_close_sumscaled(n(zt.grad), wantg, scale, rtol=2e-5, what="edge_softmax bwd")
+
+
+def test_edge_softmax_norm_by_src(oracle, cuda):
+    og, g, src, dst = graphs(oracle, 100, 100, 1500, seed=4)
+    z = np.random.default_rng(4).standard_normal((1500, 2)).astype(np.float32)
+    want = oracle.edge_softmax(og.reverse(), z)
+    np.testing.assert_allclose(n(dgl.ops.edge_softmax(g, t(z), norm_by="src")), want, rtol=1e-5)
+
+
+def _gat_reference_fp64(src, dst, n_dst, ft, el, er, slope, mask=None):
+    """fp64 torch autograd restatement (CPU): returns rst and a function computing grads."""
+    ft = torch.tensor(ft, dtype=torch.float64, requires_grad=True)
+    el = torch.tensor(el, dtype=torch.float64, requires_grad=True)
+    er = torch.tensor(er, dtype=torch.float64, requires_grad=True)
+    s, d = torch.from_numpy(src).long(), torch.from_numpy(dst).long()
+    e = torch.nn.functional.leaky_relu(el[s] + er[d], slope)            # (E,H)
+    m = torch.full((n_dst, e.shape[1]), -float("inf"), dtype=torch.float64)
+    m = m.scatter_reduce(0, d[:, None].expand_as(e), e.detach(), "amax", include_self=True)
+    ex = torch.exp(e - m[d])
+    z = torch.zeros_like(m).index_add_(0, d, ex)
+    a = ex / z[d]
+    if mask is not None:
+        a = a * torch.tensor(mask, dtype=torch.float64)
+    rst = torch.zeros((n_dst,) + ft.shape[1:], dtype=torch.float64).index_add_(0, d, a[:, :, None] * ft[s])
+    return rst, (ft, el, er), a
+
+
+@pytest.mark.parametrize("H,F", [(4, 16), (8, 8), (1, 7), (4, 40), (1, 16), (1, 41), (2, 3), (8, 64)])
+@pytest.mark.parametrize("kind", ["uniform", "powerlaw"])
+def test_gat_fused_forward_backward(oracle, cuda, H, F, kind):
+    nn_, ne = (1500, 120000) if kind == "powerlaw" else (400, 5000)
+    og, g, src, dst = graphs(oracle, nn_, nn_, ne, seed=H * 100 + F, kind=kind, self_loops=True)
+    rng = np.random.default_rng(F)
+    ft = rng.standard_normal((nn_, H, F)).astype(np.float32)
+    el = rng.standard_normal((nn_, H)).astype(np.float32)
+    er = rng.standard_normal((nn_, H)).astype(np.float32)
+    ftt, elt, ert = (t(x).requires_grad_(True) for x in (ft, el, er))
+    rst = dgl.ops.gat_attention(g, ftt, elt, ert, 0.2)
+    # forward vs the oracle's composite (u_add_v -> lrelu -> edge_softmax -> u_mul_e_sum)
+    e = oracle.gsddmm(og, "add", el[:, :, None], er[:, :, None])
+    e = np.where(e > 0, e, e * np.float32(0.2)).astype(np.float32)
+    a = oracle.edge_softmax(og, e)
+    want = oracle.gspmm(og, "mul", "sum", ft, a)
+    scale = np.zeros((nn_, H, F))
+    np.add.at(scale, dst, np.abs(a.astype(np.float64) * ft[src]))
+    assert_close_sumscaled(n(rst), want, scale, rtol=1e-5, what="gat fwd")
+    # backward vs fp64 autograd of the written-out math
+    gout = rng.standard_normal((nn_, H, F)).astype(np.float32)
+    rst.backward(t(gout))
+    ref, (rft, rel, rer), ra = _gat_reference_fp64(src, dst, nn_, ft, el, er, 0.2)
+    ref.backward(torch.tensor(gout, dtype=torch.float64))
+    a64 = ra.detach().numpy()
+    g64 = gout.astype(np.float64)
+    # grad_ft[u] = sum_{u->v} a * dZ[v]
+    sc = np.zeros((nn_, H, F))
+    np.add.at(sc, src, np.abs(a64[:, :, None] * g64[dst]))
+    assert_close_sumscaled(n(ftt.grad), rft.grad.numpy(), sc, rtol=2e-5, what="grad_ft")
+    # grad_el / grad_er: sums of a*(dd - s1) terms
+    dd = (np.abs(ft[src].astype(np.float64) * g64[dst])).sum(-1)        # (E,H) sum |terms| of the dot
+    s1 = np.zeros((nn_, H))
+    np.add.at(s1, dst, a64 * dd)
+    term = a64 * (dd + s1[dst])
+    sc_l = np.zeros((nn_, H))
+    np.add.at(sc_l, src, term)
+    sc_r = np.zeros((nn_, H))
+    np.add.at(sc_r, dst, term)
+    assert_close_sumscaled(n(elt.grad), rel.grad.numpy(), sc_l, rtol=5e-5, what="grad_el")
+    assert_close_sumscaled(n(ert.grad), rer.grad.numpy(), sc_r, rtol=5e-5, what="grad_er")
+
+
+def test_gat_fused_scores_and_row_stats(oracle, cuda):
+    from dgl import sparse as K
+    og, g, src, dst = graphs(oracle, 300, 300, 4000, seed=2, self_loops=True)
+    rng = np.random.default_rng(2)
+    ft = rng.standard_normal((300, 4, 16)).astype(np.float32)
+    el = rng.standard_normal((300, 4)).astype(np.float32)
+    er = rng.standard_normal((300, 4)).astype(np.float32)
+    rst, row_max, row_sum, scores = K._gat_fwd(g._graph, t(ft), t(el), t(er), 0.2, 0.0, 0, want_scores=True)
+    e = oracle.gsddmm(og, "add", el[:, :, None], er[:, :, None])
+    e = np.where(e > 0, e, e * np.float32(0.2)).astype(np.float32)
+    a = oracle.edge_softmax(og, e)
+    np.testing.assert_allclose(n(scores), a[:, :, 0], rtol=1e-5)
+    mx, _ = oracle.gspmm_with_args(og, "copy_rhs", "max", None, e)
+    assert np.array_equal(n(row_max), mx[:, :, 0])      # max is exact
+
+
+def test_gat_fused_dropout_is_replayed_in_backward(oracle, cuda):
+    """attn_drop: the mask comes from a counter hash of (seed, edge, head); forward with p>0 must
+    equal the p=0 math with that mask applied, and the backward must use the same mask."""
+    from dgl import sparse as K
+    nn_, ne, H, F, p = 300, 4000, 4, 8, 0.3
+    og, g, src, dst = graphs(oracle, nn_, nn_, ne, seed=11, self_loops=True)
+    rng = np.random.default_rng(11)
+    ft = rng.standard_normal((nn_, H, F)).astype(np.float32)
+    el = rng.standard_normal((nn_, H)).astype(np.float32)
+    er = rng.standard_normal((nn_, H)).astype(np.float32)
+    # recover the mask from the kernel itself: ft = one-hot of the source id is too big; instead use
+    # two forward passes with F=1 features = 1 and compare dropped vs undropped sums per edge via scores
+    ftt, elt, ert = (t(x).requires_grad_(True) for x in (ft, el, er))
+    rst = dgl.ops.gat_attention(g, ftt, elt, ert, 0.2, dropout_p=p, seed=1234)
+    rst2 = dgl.ops.gat_attention(g, t(ft), t(el), t(er), 0.2, dropout_p=p, seed=1234)
+    assert torch.equal(rst, rst2)                        # deterministic given the seed
+    rst3 = dgl.ops.gat_attention(g, t(ft), t(el), t(er), 0.2, dropout_p=p, seed=99)
+    assert not torch.equal(rst, rst3)
+    # mask recovery: grad of sum(rst[:, h, 0]) wrt a is linear; use a probe graph-wide instead:
+    # run with ft = 1 and F = 1 -> rst[v,h] = sum_j a_j * drop_j ; compare with scores to count kept mass
+    ones = torch.ones((nn_, H, 1), device=cuda)
+    kept = dgl.ops.gat_attention(g, ones, t(el), t(er), 0.2, dropout_p=p, seed=1234)[:, :, 0]
+    frac = (n(kept) * (1 - p)).mean()                    # E[sum_j a_j * keep_j] = 1 - p
+    assert abs(frac - (1 - p)) < 0.03
+    # backward consistency: finite-difference-free check via linearity in ft:
+    gout = rng.standard_normal((nn_, H, F)).astype(np.float32)
+    rst.backward(t(gout))
+    # d/d ft of <rst, gout> evaluated by a second forward on basis direction: <rst(ft + eps*dir) - rst(ft), gout>/eps
+    direction = rng.standard_normal((nn_, H, F)).astype(np.float32)
+    r_plus = dgl.ops.gat_attention(g, t(ft + direction), t(el), t(er), 0.2, dropout_p=p, seed=1234)
+    lhs = ((r_plus - rst2) * t(gout)).sum().item()       # exact: rst is linear in ft
+    rhs = (ftt.grad * t(direction)).sum().item()
+    assert abs(lhs - rhs) <= 1e-3 * (abs(lhs) + 1)
+
+
+def test_gat_zero_in_degree_rows(oracle, cuda):
+    g = dgl.graph((torch.tensor([0, 1]), torch.tensor([2, 2])), num_nodes=4).int().to(cuda)
+    ft = torch.ones((4, 2, 3), device=cuda, requires_grad=True)
+    el = torch.zeros((4, 2), device=cuda, requires_grad=True)
+    er = torch.zeros((4, 2), device=cuda, requires_grad=True)
+    rst = dgl.ops.gat_attention(g, ft, el, er, 0.2)
+    assert n(rst)[2].tolist() == [[1, 1, 1], [1, 1, 1]] and n(rst)[[0, 1, 3]].sum() == 0
+    rst.sum().backward()
+    assert np.allclose(n(ft.grad)[0], 0.5) and np.allclose(n(ft.grad)[2:], 0)

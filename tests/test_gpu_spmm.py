@@ -1,0 +1,160 @@
+"""-m gpu parity: dgl.ops.gspmm through the C-ABI vs the CPU oracle on the same seeded inputs.
+Bit-exact: structure-derived outputs (arg_u/arg_e incl. first-wins ties, zero-degree handling) and,
+for rows that are not split, the sums themselves (same sequential fp32 order as SpMMSumCsr).
+Tolerance otherwise: |a-b| <= 1e-5 * sum|terms| (north_star: 1e-5 relative in fp32)."""
+import numpy as np
+import pytest
+import torch
+
+import dgl
+from conftest import assert_close_sumscaled
+from gpu_util import abs_sum_scale_spmm, graphs, n, t
+
+pytestmark = pytest.mark.gpu
+
+WIDTHS = [1, 2, 3, 4, 7, 16, 33, 64, 100, 128, 256, 602]
+
+
+@pytest.mark.parametrize("D", WIDTHS)
+@pytest.mark.parametrize("reduce_op", ["sum", "mean", "max", "min"])
+def test_copy_u(oracle, cuda, D, reduce_op):
+    og, g, src, dst = graphs(oracle, 300, 260, 6000, seed=D)
+    X = np.random.default_rng(D).random((300, D), dtype=np.float32)
+    want = oracle.gspmm(og, "copy_lhs", reduce_op, X, None)
+    got = n(dgl.ops.gspmm(g, "copy_lhs", reduce_op, t(X), None))
+    # no hub rows at this size: every row is accumulated sequentially in CSC order => bit-exact
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("D", [1433])
+def test_copy_u_cora_width(oracle, cuda, D):
+    og, g, src, dst = graphs(oracle, 2708, 2708, 10556, seed=0)
+    X = np.random.default_rng(0).random((2708, D), dtype=np.float32)
+    for r in ("sum", "mean"):
+        assert np.array_equal(n(dgl.ops.gspmm(g, "copy_lhs", r, t(X), None)), oracle.gspmm(og, "copy_lhs", r, X, None))
+
+
+@pytest.mark.parametrize("D", [1, 4, 8, 64, 256])
+@pytest.mark.parametrize("reduce_op", ["sum", "max", "min", "mean"])
+def test_copy_e(oracle, cuda, D, reduce_op):
+    og, g, src, dst = graphs(oracle, 200, 150, 3000, seed=D + 1)
+    W = np.random.default_rng(D).standard_normal((3000, D)).astype(np.float32)
+    want = oracle.gspmm(og, "copy_rhs", reduce_op, None, W)
+    got = n(dgl.ops.gspmm(g, "copy_rhs", reduce_op, None, t(W)))
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("shape", [((64,), (64,)), ((4, 16), (4, 1)), ((8, 8), (8, 1)), ((1, 7), (1, 1)),
+                                   ((100,), (1,)), ((4, 40), (4, 1)), ((3, 5), (3, 5)), ((6,), (1,))])
+def test_u_mul_e_sum(oracle, cuda, shape):
+    ls, rs = shape
+    og, g, src, dst = graphs(oracle, 220, 220, 4000, seed=len(ls) + ls[-1])
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((220,) + ls).astype(np.float32)
+    W = rng.standard_normal((4000,) + rs).astype(np.float32)
+    want = oracle.gspmm(og, "mul", "sum", X, W)
+    got = n(dgl.ops.gspmm(g, "mul", "sum", t(X), t(W)))
+    assert np.array_equal(got, want)  # mul and add are not contracted: same bits as the CPU kernel
+
+
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "div"])
+@pytest.mark.parametrize("reduce_op", ["sum", "max", "min"])
+def test_generic_broadcast_path(oracle, cuda, op, reduce_op):
+    """Shapes the vector kernels do not cover go through the generic kernel, same results."""
+    og, g, src, dst = graphs(oracle, 90, 70, 1200, seed=17)
+    rng = np.random.default_rng(2)
+    X = (rng.random((90, 3, 1)) + 0.5).astype(np.float32)
+    W = (rng.random((1200, 1, 5)) + 0.5).astype(np.float32)
+    want = oracle.gspmm(og, op, reduce_op, X, W)
+    got = n(dgl.ops.gspmm(g, op, reduce_op, t(X), t(W)))
+    scale = abs_sum_scale_spmm(src, dst, 70, np.ones((1200, 3, 5)) * 4)
+    assert_close_sumscaled(got, want, scale + 1, rtol=1e-6, what="%s/%s" % (op, reduce_op))
+
+
+@pytest.mark.parametrize("op,D", [("copy_lhs", 5), ("copy_lhs", 64), ("copy_rhs", 16), ("mul", 12)])
+def test_argmax_bit_exact_with_ties(oracle, cuda, op, D):
+    from dgl import sparse as K
+    og, g, src, dst = graphs(oracle, 150, 120, 5000, seed=D)
+    rng = np.random.default_rng(D)
+    X = rng.integers(0, 3, size=(150, D)).astype(np.float32)   # few distinct values => many ties
+    W = rng.integers(1, 3, size=(5000, D)).astype(np.float32)
+    for red in ("max", "min"):
+        want, (wu, we) = oracle.gspmm_with_args(og, op, red, X if op != "copy_rhs" else None,
+                                                W if op != "copy_lhs" else None)
+        got, (gu, ge) = K._gspmm(g._graph, op, red, t(X) if op != "copy_rhs" else None,
+                                 t(W) if op != "copy_lhs" else None)
+        assert np.array_equal(n(got), want)
+        if wu is not None:
+            assert np.array_equal(n(gu), wu)
+        if we is not None:
+            assert np.array_equal(n(ge), we)
+
+
+@pytest.mark.parametrize("D", [4, 64, 256, 602])
+@pytest.mark.parametrize("reduce_op", ["sum", "mean", "max"])
+def test_hub_rows_power_law(oracle, cuda, D, reduce_op):
+    """Power-law graph whose hubs exceed the split threshold: split rows are within tolerance,
+    unsplit rows stay bit-exact, arg-max stays exact (ties still resolve to the first CSC entry)."""
+    from dgl import sparse as K
+    from dgl import _capi
+    og, g, src, dst = graphs(oracle, 3000, 3000, 200000, seed=5, kind="powerlaw")
+    X = np.random.default_rng(3).integers(0, 5, size=(3000, D)).astype(np.float32) if reduce_op == "max" \
+        else np.random.default_rng(3).random((3000, D), dtype=np.float32)
+    thr = _capi.lib().dglb_default_hub_threshold(D)
+    deg = og.in_degrees()
+    hub = deg > thr
+    if D >= 64:
+        assert hub.any(), "test graph must contain hub rows"
+    if reduce_op == "max":
+        want, (wu, _) = oracle.gspmm_with_args(og, "copy_lhs", "max", X, None)
+        got, (gu, _) = K._gspmm(g._graph, "copy_lhs", "max", t(X), None)
+        assert np.array_equal(n(got), want) and np.array_equal(n(gu), wu)
+        return
+    want = oracle.gspmm(og, "copy_lhs", reduce_op, X, None)
+    got = n(dgl.ops.gspmm(g, "copy_lhs", reduce_op, t(X), None))
+    assert np.array_equal(got[~hub], want[~hub])
+    scale = abs_sum_scale_spmm(src, dst, 3000, np.abs(X[src]))
+    if reduce_op == "mean":
+        scale = scale / np.maximum(deg, 1)[:, None]
+    assert_close_sumscaled(got, want, scale, rtol=1e-5, what="hub rows")
+
+
+def test_bipartite_block(oracle, cuda):
+    og, g, src, dst = graphs(oracle, 500, 120, 4000, seed=9)
+    X = np.random.default_rng(9).random((500, 32), dtype=np.float32)
+    assert np.array_equal(n(dgl.ops.gspmm(g, "copy_lhs", "sum", t(X), None)), oracle.gspmm(og, "copy_lhs", "sum", X, None))
+
+
+def test_zero_degree_rows_and_empty_graph(oracle, cuda):
+    g = dgl.graph((torch.tensor([0, 0]), torch.tensor([3, 3])), num_nodes=5).int().to(cuda)
+    X = torch.arange(10, dtype=torch.float32, device=cuda).reshape(5, 2)
+    assert n(dgl.ops.gspmm(g, "copy_lhs", "sum", X, None)).tolist() == [[0, 0], [0, 0], [0, 0], [0, 2], [0, 0]]
+    assert n(dgl.ops.gspmm(g, "copy_lhs", "max", X, None)).tolist() == [[0, 0], [0, 0], [0, 0], [0, 1], [0, 0]]
+    assert n(dgl.ops.gspmm(g, "copy_lhs", "mean", X, None)).tolist() == [[0, 0], [0, 0], [0, 0], [0, 1], [0, 0]]
+    e = dgl.graph((torch.zeros(0, dtype=torch.int64), torch.zeros(0, dtype=torch.int64)), num_nodes=3).int().to(cuda)
+    assert n(dgl.ops.gspmm(e, "copy_lhs", "sum", X[:3], None)).tolist() == [[0, 0]] * 3
+
+
+def test_scalar_features_are_squeezed_back(oracle, cuda):
+    og, g, src, dst = graphs(oracle, 60, 60, 500, seed=2)
+    x = np.random.default_rng(0).random(60, dtype=np.float32)
+    w = np.random.default_rng(1).random(500, dtype=np.float32)
+    got = dgl.ops.gspmm(g, "mul", "sum", t(x), t(w))
+    assert got.shape == (60,)
+    assert np.array_equal(n(got), oracle.gspmm(og, "mul", "sum", x, w))
+
+
+def test_known_answer_vector(oracle, cuda):
+    import json, os
+    G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "appendix_a6.json")))
+    g = dgl.graph((torch.tensor(G["src"]), torch.tensor(G["dst"])), num_nodes=G["n"]).int().to(cuda)
+    X = torch.tensor(G["X"], dtype=torch.float32, device=cuda)
+    assert n(dgl.ops.gspmm(g, "copy_lhs", "sum", X, None)).tolist() == G["copy_u_sum"]
+    assert n(dgl.ops.gspmm(g, "copy_lhs", "mean", X, None)).tolist() == G["copy_u_mean"]
+    assert n(dgl.ops.gspmm(g, "copy_lhs", "max", X, None)).tolist() == G["copy_u_max"]
+    assert n(dgl.ops.gsddmm(g, "dot", X, X)).reshape(-1).tolist() == G["u_dot_v"]
+    z = torch.tensor(G["edge_softmax_logits_div4"], dtype=torch.float32, device=cuda) / 4
+    np.testing.assert_allclose(n(dgl.ops.edge_softmax(g, z)), G["edge_softmax"], atol=5e-7)
+    assert n(g._graph.csc().indptr).tolist() == G["csc_indptr"]
+    assert n(g._graph.csc().indices).tolist() == G["csc_indices"]
+    assert n(g._graph.csc().eids).tolist() == G["csc_data"]
