@@ -210,23 +210,24 @@ def main():
         feats[D] = (torch.rand(rows, D, device=dev), torch.rand(rows, D, device=dev))
     host = None
 
-    ev = {"spmm602": []}
+    ev = {}  # (op, D) -> [(start, end)] CUDA events around each launch inside the timed region
+
+    def timed(key, record, fn):
+        if not record:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        ev.setdefault(key, []).append((a, b))
+        return r
 
     def one_step(record=False):
         for D in WIDTHS:
             X, V = feats[D]
-            if part is not None:
-                Xfull = part.all_gather_rows(X)
-            else:
-                Xfull = X
-            if record and D == 602:
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record()
-            out = dgl.ops.gspmm(g, "copy_lhs", "sum", Xfull, None)
-            if record and D == 602:
-                b.record()
-                ev["spmm602"].append((a, b))
-            sc = dgl.ops.gsddmm(g, "dot", Xfull, V)
+            Xfull = part.all_gather_rows(X) if part is not None else X
+            out = timed(("gspmm_copy_u_sum", D), record, lambda: dgl.ops.gspmm(g, "copy_lhs", "sum", Xfull, None))
+            sc = timed(("gsddmm_u_dot_v", D), record, lambda: dgl.ops.gsddmm(g, "dot", Xfull, V))
         return out, sc
 
     def barrier():
@@ -249,7 +250,8 @@ def main():
             barrier()
         ms = start.elapsed_time(end) / args.steps
         launches = _capi.launches() - l0
-        k_ms = float(np.mean([a.elapsed_time(b) for a, b in ev["spmm602"]]))
+        per_kernel = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in ev.items()}
+        k_ms = per_kernel[("gspmm_copy_u_sum", 602)]
 
         # ---- e2e: host inputs, H2D + compute + D2H inside the timed region (public API)
         rows = n_dst_local if part is not None else N_NODES
@@ -309,7 +311,13 @@ def main():
             "e2e": {"value": e2e_val, "unit": "GB/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
             "gpu_launches": launches, "clocks": clocks.summary(),
-            "edges_per_s": 8 * N_EDGES / (ms * 1e-3)}
+            "edges_per_s": 8 * N_EDGES / (ms * 1e-3),
+            "kernels": [{"op": op, "D": D, "ms": t_ms,
+                         "algorithmic_gbs": (spmm_bytes(n_dst_local, n_edges_local, D) if op.startswith("gspmm")
+                                             else sddmm_dot_bytes(n_dst_local, n_edges_local, D)) / (t_ms * 1e-3) / 1e9}
+                        for (op, D), t_ms in sorted(per_kernel.items())]}
+    for k in line["kernels"]:
+        k["frac_of_peak"] = k["algorithmic_gbs"] / peak
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_arm(1, 0, budget_s=15.0)
         line["cpu_baseline"] = cb

@@ -13,6 +13,16 @@ from ._capi import DGLError
 
 _TARGET = _capi.TARGETS
 
+# Rows with more nnz than this are handled by the split-row ("hub") kernels.  None = the library's
+# width-dependent default (dglb_default_hub_threshold); tests lower it to exercise the hub path.
+HUB_THRESHOLD = None
+
+
+def _hub_threshold(width):
+    if HUB_THRESHOLD is not None:
+        return int(HUB_THRESHOLD)
+    return _capi.lib().dglb_default_hub_threshold(int(width))
+
 
 def infer_broadcast_shape(op, shp1, shp2):
     """Feature shape of op(lhs, rhs) under numpy-style broadcasting of the per-node / per-edge
@@ -111,7 +121,7 @@ def _gspmm(gidx, op, reduce_op, u, e, row_scale=None):
         for s in feat_shape:
             out_len *= s
         l = _capi.lib()
-        thr = l.dglb_default_hub_threshold(out_len)
+        thr = _hub_threshold(out_len)
         hub_rows, n_hub = csc.hubs(thr)
         ndim, ls, rs = _shapes_for_abi(op, u, e)
         stream = _capi.enter(dev)
@@ -183,7 +193,7 @@ def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
             width = 1
             for s in ref.shape[1:]:
                 width *= s
-            thr = l.dglb_default_hub_threshold(width)
+            thr = _hub_threshold(width)
             hub_rows, n_hub = csc.hubs(thr)
             rc = l.dglb_gsddmm_csr(_capi.OPS[op], _capi.F32, lt, rt, csc.n_rows, csc.n_cols, csc.nnz,
                                    _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(csc.eids),
@@ -216,7 +226,7 @@ def _edge_softmax_fwd(gidx, logits):
     heads = logits.numel() // gidx.n_edges
     csc = gidx.csc()
     l = _capi.lib()
-    thr = l.dglb_default_hub_threshold(max(heads, 64))
+    thr = _hub_threshold(max(heads, 64))
     hub_rows, n_hub = csc.hubs(thr)
     stream = _capi.enter(dev)
     rc = l.dglb_edge_softmax_fwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(csc.eids),
@@ -237,7 +247,7 @@ def _edge_softmax_bwd(gidx, out, grad_out):
     heads = out.numel() // gidx.n_edges
     csc = gidx.csc()
     l = _capi.lib()
-    thr = l.dglb_default_hub_threshold(max(heads, 64))
+    thr = _hub_threshold(max(heads, 64))
     hub_rows, n_hub = csc.hubs(thr)
     stream = _capi.enter(dev)
     rc = l.dglb_edge_softmax_bwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(csc.eids),
@@ -263,7 +273,7 @@ def _gat_fwd(gidx, ft, el, er, slope, dropout_p, seed, want_scores=False):
         return rst, row_max, row_sum, scores
     csc = gidx.csc()
     l = _capi.lib()
-    thr = l.dglb_default_hub_threshold(H * F)
+    thr = _hub_threshold(H * F)
     hub_rows, n_hub = csc.hubs(thr)
     stream = _capi.enter(dev)
     rc = l.dglb_gat_fused_fwd(_capi.F32, csc.n_rows, csc.n_cols, csc.nnz, H, F, float(slope), float(dropout_p),
@@ -286,7 +296,7 @@ def _gat_bwd(gidx, ft, el, er, row_max, row_sum, grad_rst, slope, dropout_p, see
     grad_ft = torch.empty_like(ft)
     grad_el = torch.empty((gidx.n_src, H), dtype=ft.dtype, device=dev)
     l = _capi.lib()
-    thr = l.dglb_default_hub_threshold(H * F)
+    thr = _hub_threshold(H * F)
     stream = _capi.enter(dev)
     if gidx.n_dst:
         hub_rows, n_hub = csc.hubs(thr)

@@ -50,3 +50,13 @@ def assert_close_sumscaled(actual, expected, scale, rtol=1e-5, what=""):
         i = np.unravel_index(np.argmax(err / bound), err.shape)
         raise AssertionError("%s: %d elements exceed %g * scale; worst at %s: got %r want %r scale %r"
                              % (what, bad.sum(), rtol, i, actual[i], expected[i], scale[i]))
+
+
+@pytest.fixture
+def small_hub_threshold():
+    """Lower the split-row threshold so modest test graphs exercise the hub kernels."""
+    from dgl import sparse as K
+    old = K.HUB_THRESHOLD
+    K.HUB_THRESHOLD = 48
+    yield 48
+    K.HUB_THRESHOLD = old

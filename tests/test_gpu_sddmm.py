@@ -97,7 +97,7 @@ def test_formats_without_coo_use_the_csr_kernels(oracle, cuda):
     assert np.array_equal(n(dgl.ops.gsddmm(g2, "mul", t(E), t(V), "e", "v")), oracle.gsddmm(og, "mul", E, V, "e", "v"))
 
 
-def test_hub_rows(oracle, cuda):
+def test_hub_rows(oracle, cuda, small_hub_threshold):
     og, g, src, dst = graphs(oracle, 3000, 3000, 200000, seed=5, kind="powerlaw")
     rng = np.random.default_rng(8)
     U = rng.standard_normal((3000, 602)).astype(np.float32)

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("H", [1, 2, 3, 4, 8, 12, 40])
 @pytest.mark.parametrize("kind", ["uniform", "powerlaw"])
-def test_edge_softmax_forward_backward(oracle, cuda, H, kind):
+def test_edge_softmax_forward_backward(oracle, cuda, H, kind, small_hub_threshold):
     ne = 60000 if kind == "powerlaw" else 4000
     nn_ = 800 if kind == "powerlaw" else 300
     og, g, src, dst = graphs(oracle, nn_, nn_, ne, seed=H, kind=kind)
@@ -63,7 +63,7 @@ def _gat_reference_fp64(src, dst, n_dst, ft, el, er, slope, mask=None):
 
 @pytest.mark.parametrize("H,F", [(4, 16), (8, 8), (1, 7), (4, 40), (1, 16), (1, 41), (2, 3), (8, 64)])
 @pytest.mark.parametrize("kind", ["uniform", "powerlaw"])
-def test_gat_fused_forward_backward(oracle, cuda, H, F, kind):
+def test_gat_fused_forward_backward(oracle, cuda, H, F, kind, small_hub_threshold):
     nn_, ne = (1500, 120000) if kind == "powerlaw" else (400, 5000)
     og, g, src, dst = graphs(oracle, nn_, nn_, ne, seed=H * 100 + F, kind=kind, self_loops=True)
     rng = np.random.default_rng(F)

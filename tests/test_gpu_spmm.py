@@ -90,9 +90,9 @@ def test_argmax_bit_exact_with_ties(oracle, cuda, op, D):
             assert np.array_equal(n(ge), we)
 
 
-@pytest.mark.parametrize("D", [4, 64, 256, 602])
+@pytest.mark.parametrize("D", [1, 4, 64, 256, 602, 1433])
 @pytest.mark.parametrize("reduce_op", ["sum", "mean", "max"])
-def test_hub_rows_power_law(oracle, cuda, D, reduce_op):
+def test_hub_rows_power_law(oracle, cuda, D, reduce_op, small_hub_threshold):
     """Power-law graph whose hubs exceed the split threshold: split rows are within tolerance,
     unsplit rows stay bit-exact, arg-max stays exact (ties still resolve to the first CSC entry)."""
     from dgl import sparse as K
@@ -100,11 +100,9 @@ def test_hub_rows_power_law(oracle, cuda, D, reduce_op):
     og, g, src, dst = graphs(oracle, 3000, 3000, 200000, seed=5, kind="powerlaw")
     X = np.random.default_rng(3).integers(0, 5, size=(3000, D)).astype(np.float32) if reduce_op == "max" \
         else np.random.default_rng(3).random((3000, D), dtype=np.float32)
-    thr = _capi.lib().dglb_default_hub_threshold(D)
     deg = og.in_degrees()
-    hub = deg > thr
-    if D >= 64:
-        assert hub.any(), "test graph must contain hub rows"
+    hub = deg > small_hub_threshold
+    assert hub.sum() > 50 and (~hub).sum() > 50, "test graph must contain hub and ordinary rows"
     if reduce_op == "max":
         want, (wu, _) = oracle.gspmm_with_args(og, "copy_lhs", "max", X, None)
         got, (gu, _) = K._gspmm(g._graph, "copy_lhs", "max", t(X), None)
@@ -158,3 +156,26 @@ def test_known_answer_vector(oracle, cuda):
     assert n(g._graph.csc().indptr).tolist() == G["csc_indptr"]
     assert n(g._graph.csc().indices).tolist() == G["csc_indices"]
     assert n(g._graph.csc().eids).tolist() == G["csc_data"]
+
+
+@pytest.mark.parametrize("shape", [((4, 16), (4, 1)), ((32,), (32,)), ((100,), (1,))])
+def test_hub_rows_u_mul_e_and_copy_e(oracle, cuda, shape, small_hub_threshold):
+    ls, rs = shape
+    og, g, src, dst = graphs(oracle, 2000, 2000, 100000, seed=6, kind="powerlaw")
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((2000,) + ls).astype(np.float32)
+    W = rng.standard_normal((100000,) + rs).astype(np.float32)
+    want = oracle.gspmm(og, "mul", "sum", X, W)
+    got = n(dgl.ops.gspmm(g, "mul", "sum", t(X), t(W)))
+    scale = abs_sum_scale_spmm(src, dst, 2000, np.abs(X[src] * W))
+    assert_close_sumscaled(got, want, scale, rtol=1e-5, what="hub u_mul_e")
+    hub = og.in_degrees() > small_hub_threshold
+    assert np.array_equal(got[~hub], want[~hub])
+    We = rng.standard_normal((100000, 8)).astype(np.float32)
+    for red in ("sum", "max", "min"):
+        want = oracle.gspmm(og, "copy_rhs", red, None, We)
+        got = n(dgl.ops.gspmm(g, "copy_rhs", red, None, t(We)))
+        if red == "sum":
+            assert_close_sumscaled(got, want, abs_sum_scale_spmm(src, dst, 2000, np.abs(We)), rtol=1e-5, what="hub copy_e")
+        else:
+            assert np.array_equal(got, want)
