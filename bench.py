@@ -132,7 +132,9 @@ def cpu_arm(steps, warmup, budget_s=20.0):
 
     def sample_bytes(rows, edges):
         e_rows = int(indptr[rows])
-        return sum(spmm_bytes(rows, e_rows, D) + (4 * edges * 2 + 4 * D * edges * 2 + 4 * edges) for D in WIDTHS)
+        # same gather-model byte count as the GPU arm (work definition, not the CPU's own traffic)
+        nd = max(1, int(round(N_NODES * edges / N_EDGES)))
+        return sum(spmm_bytes(rows, e_rows, D) + sddmm_dot_bytes(nd, edges, D) for D in WIDTHS)
 
     # calibrate on 1/64 of the rows / edges, then size the sample for ~budget_s/(steps+warmup) per step
     r0, m0 = N_NODES // 64, N_EDGES // 64

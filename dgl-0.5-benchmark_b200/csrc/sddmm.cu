@@ -71,25 +71,57 @@ __device__ __forceinline__ void group_work(const SddmmParams& p, int64_t& row, i
 }
 
 // ------------------------------------------------------------------ dot
-template <int VEC, int CH, bool HUB>
+// Reduce U per-lane partial sums across a group of G = 2^LOGG lanes with a "transposing" butterfly:
+// each exchange step halves the number of live values per lane (lanes whose `mask` bit is set keep
+// the upper half), so U values cost (U-1) + log2(G/U) shuffles instead of U*log2(G).  Afterwards
+// lane lg holds, in v[0..max(1,U/G)), the totals of edges ((lg*U) >> LOGG) + i.
+template <int U, int LOGG>
+__device__ __forceinline__ void group_transpose_reduce(float (&v)[U], int lg) {
+  constexpr int G = 1 << LOGG;
+  int cnt = U;
+#pragma unroll
+  for (int mask = G >> 1; mask >= 1; mask >>= 1) {
+    if (cnt > 1) {
+      const int half = cnt >> 1;
+      const bool up = (lg & mask) != 0;
+#pragma unroll
+      for (int i = 0; i < U / 2; ++i) {
+        if (i < half) {
+          const float send = up ? v[i] : v[i + half];
+          const float keep = up ? v[i + half] : v[i];
+          v[i] = keep + __shfl_xor_sync(FULL_MASK, send, mask);
+        }
+      }
+      cnt = half;
+    } else {
+      v[0] += __shfl_xor_sync(FULL_MASK, v[0], mask);
+    }
+  }
+}
+
+__host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
+
+// LOGG >= 0: single output column, G = 2^LOGG known at compile time (transposing reduction).
+// LOGG == -1: (N,H,F) operands, runtime G and `seg` lanes per head (segmented butterfly).
+// SINGLE: the whole row fits one feature tile, so the destination row lives in registers.
+template <int VEC, int CH, int LOGG, bool SINGLE, bool HUB>
 __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmParams p) {
   constexpr int U = 8 / CH;
-  const int G = p.G;
+  const int G = LOGG >= 0 ? (1 << LOGG) : p.G;
   const int lg = threadIdx.x & (G - 1);
   int64_t row, j0;
   int n;
   group_work<HUB>(p, row, j0, n);
   const int nmax = __reduce_max_sync(FULL_MASK, n);
   const int tile_cols = G * CH;
-  const bool single = p.ncols <= tile_cols;
   const float* __restrict__ vrow = p.V + row * (int64_t)p.D;
   FVec<VEC> vreg[CH];
+  if constexpr (SINGLE) {
 #pragma unroll
-  for (int c = 0; c < CH; ++c) {
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) vreg[c].v[v] = 0.f;
-    const int vc = c * G + lg;
-    if (single && n > 0 && vc < p.ncols) vreg[c] = ldg_vec<VEC>(vrow + vc * VEC);
+    for (int c = 0; c < CH; ++c) {
+      const int vc = c * G + lg;
+      if (n > 0 && vc < p.ncols) vreg[c] = ldg_vec<VEC>(vrow + vc * VEC);
+    }
   }
   for (int off = 0; off < nmax; off += G) {
     const int m = min(max(n - off, 0), G);
@@ -101,54 +133,72 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmPar
     }
     const int mmax = min(G, nmax - off);
     for (int t = 0; t < mmax; t += U) {
-      int cc[U], ee[U];
+      int cc[U];
       float part[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         cc[u] = __shfl_sync(FULL_MASK, my_c, t + u, G);
-        ee[u] = __shfl_sync(FULL_MASK, my_e, t + u, G);
         part[u] = 0.f;
       }
-      for (int tile0 = 0; tile0 < p.ncols; tile0 += tile_cols) {
+      for (int tile0 = 0; tile0 < (SINGLE ? 1 : p.ncols); tile0 += tile_cols) {
         FVec<VEC> xv[U][CH];
         FVec<VEC> vv[CH];
+        bool colv[CH];
+        // phase 1: issue every load of this (edge batch, tile) before the first use
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           const int vc = tile0 + c * G + lg;
-          if (single) vv[c] = vreg[c];
-          else if (vc < p.ncols && m > 0) vv[c] = ldg_vec<VEC>(vrow + vc * VEC);
-          else {
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) vv[c].v[v] = 0.f;
+          colv[c] = vc < p.ncols;
+          if constexpr (!SINGLE) {
+            if (colv[c] && m > 0) vv[c] = ldg_vec<VEC>(vrow + vc * VEC);
           }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const bool valid = (t + u) < m;
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
-            const int vc = tile0 + c * G + lg;
-            if (valid && vc < p.ncols) {
-              xv[u][c] = ldg_vec<VEC>(p.U + (int64_t)cc[u] * p.D + vc * VEC);
-            } else {
+            if ((t + u) < m && colv[c])
+              xv[u][c] = ldg_vec<VEC>(p.U + (int64_t)cc[u] * p.D + (tile0 + c * G + lg) * VEC);
+          }
+        }
+        // phase 2: multiply-accumulate
 #pragma unroll
-              for (int v = 0; v < VEC; ++v) xv[u][c].v[v] = 0.f;
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            if ((t + u) < m && colv[c]) {
+#pragma unroll
+              for (int v = 0; v < VEC; ++v)
+                part[u] = fmaf(xv[u][c].v[v], SINGLE ? vreg[c].v[v] : vv[c].v[v], part[u]);
             }
           }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-          for (int c = 0; c < CH; ++c)
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) part[u] = fmaf(xv[u][c].v[v], vv[c].v[v], part[u]);
       }
-      // segmented butterfly: seg lanes per head (seg == G when there is one head)
+      if constexpr (LOGG >= 0) {
+        group_transpose_reduce<U, LOGG>(part, lg);
+        constexpr int GG = 1 << LOGG;
+        if constexpr (GG >= U) {
+          const int u_l = lg >> (LOGG - ilog2(U));
+          const int e = __shfl_sync(FULL_MASK, my_e, t + u_l, GG);
+          if ((lg & (GG / U - 1)) == 0 && (t + u_l) < m) p.out[e] = part[0];
+        } else {
+          constexpr int CF = U / GG;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        for (int s = p.seg >> 1; s > 0; s >>= 1) part[u] += __shfl_xor_sync(FULL_MASK, part[u], s);
-        if ((t + u) < m && (lg & (p.seg - 1)) == 0 && (lg / p.seg) < p.H)
-          p.out[(int64_t)ee[u] * p.H + (lg / p.seg)] = part[u];
+          for (int i = 0; i < CF; ++i) {
+            const int u_l = lg * CF + i;
+            const int e = __shfl_sync(FULL_MASK, my_e, t + u_l, GG);
+            if ((t + u_l) < m) p.out[e] = part[i];
+          }
+        }
+      } else {
+        // segmented butterfly: seg lanes per head
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int e = __shfl_sync(FULL_MASK, my_e, t + u, G);
+          for (int s = p.seg >> 1; s > 0; s >>= 1) part[u] += __shfl_xor_sync(FULL_MASK, part[u], s);
+          if ((t + u) < m && (lg & (p.seg - 1)) == 0 && (lg / p.seg) < p.H)
+            p.out[(int64_t)e * p.H + (lg / p.seg)] = part[u];
+        }
       }
     }
   }
@@ -289,19 +339,37 @@ int sddmm_generic_f32(const GenericSddmmParams& g, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------ dispatch
-template <int VEC, int CH>
+template <int VEC, int CH, int LOGG, bool SINGLE>
 static int launch_dot(const SddmmParams& p, int n_hub, cudaStream_t stream) {
   const int rows_per_block = kBlockThreads / p.G;
   const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
   if (blocks > 0) {
-    sddmm_dot_kernel<VEC, CH, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+    sddmm_dot_kernel<VEC, CH, LOGG, SINGLE, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
     DGLB_LAUNCH_CHECK("sddmm_dot_kernel");
   }
   if (n_hub > 0) {
-    sddmm_dot_kernel<VEC, CH, true><<<n_hub, kBlockThreads, 0, stream>>>(p);
+    sddmm_dot_kernel<VEC, CH, LOGG, SINGLE, true><<<n_hub, kBlockThreads, 0, stream>>>(p);
     DGLB_LAUNCH_CHECK("sddmm_dot_kernel(hub)");
   }
   return DGLB_OK;
+}
+
+template <int VEC>
+static int dispatch_dot(const SddmmParams& p, int ch, int n_hub, cudaStream_t stream) {
+  const bool single = p.ncols <= p.G * ch;
+  if (p.H > 1) return launch_dot<VEC, 1, -1, true>(p, n_hub, stream);  // caller guarantees ch == 1
+  if (ch == 1) {
+    switch (p.log2G) {
+      case 0: return launch_dot<VEC, 1, 0, true>(p, n_hub, stream);
+      case 1: return launch_dot<VEC, 1, 1, true>(p, n_hub, stream);
+      case 2: return launch_dot<VEC, 1, 2, true>(p, n_hub, stream);
+      case 3: return launch_dot<VEC, 1, 3, true>(p, n_hub, stream);
+      case 4: return launch_dot<VEC, 1, 4, true>(p, n_hub, stream);
+      default: return launch_dot<VEC, 1, 5, true>(p, n_hub, stream);
+    }
+  }
+  if (ch == 2) return single ? launch_dot<VEC, 2, 5, true>(p, n_hub, stream) : launch_dot<VEC, 2, 5, false>(p, n_hub, stream);
+  return single ? launch_dot<VEC, 4, 5, true>(p, n_hub, stream) : launch_dot<VEC, 4, 5, false>(p, n_hub, stream);
 }
 
 template <int VEC, int CH, int OP>
@@ -371,12 +439,9 @@ int sddmm_csr_fast_f32(int op, int64_t n_dst, const int32_t* indptr, const int32
   const int ch = per_lane >= 4 ? 4 : (per_lane >= 2 ? 2 : 1);
   if (op == DGLB_OP_DOT) {
     if (p.H > 1 && ch != 1) return DGLB_E_UNSUPPORTED;
-#define DGLB_CASE(V, C) if (vec == V && ch == C) return launch_dot<V, C>(p, n_hub, stream);
-    DGLB_CASE(4, 1) DGLB_CASE(4, 2) DGLB_CASE(4, 4)
-    DGLB_CASE(2, 1) DGLB_CASE(2, 2) DGLB_CASE(2, 4)
-    DGLB_CASE(1, 1) DGLB_CASE(1, 2) DGLB_CASE(1, 4)
-#undef DGLB_CASE
-    return DGLB_E_UNSUPPORTED;
+    if (vec == 4) return dispatch_dot<4>(p, ch, n_hub, stream);
+    if (vec == 2) return dispatch_dot<2>(p, ch, n_hub, stream);
+    return dispatch_dot<1>(p, ch, n_hub, stream);
   }
   switch (op) {
     case DGLB_OP_ADD: return dispatch_ew<DGLB_OP_ADD>(p, vec, ch, n_hub, stream);
