@@ -1,0 +1,149 @@
+"""1-D row partition of a full-graph workload across the GPUs of one node (one process per GPU,
+torch.distributed over NCCL / NVLink; gloo on CPU for the host-logic tests).
+
+New relative to the reference (single V100, no torch.distributed anywhere -- SURVEY.md 2.1); required
+by BASELINE.json's north_star.  Scheme:
+
+  * nodes are split into P contiguous ranges balanced by in-edge count (prefix sum of in-degrees);
+    rank r owns the destination rows [lo_r, hi_r), their feature rows, labels and masks;
+  * forward aggregation  out[v] = sum_{u->v} X[u]  for v in the rank's range needs X of every source:
+    the ranks all-gather their feature rows (each row crosses NVLink once per rank, which beats
+    per-edge peer loads by the average in-degree / P on these graphs), then run the SAME gspmm kernel
+    on their slice of the CSC -- a block graph with N global sources and (hi-lo) local destinations;
+  * backward  dX[u] = sum_{u->v} dZ[v]  for u in the rank's range: all-gather dZ, then gspmm on the
+    rank's slice of the CSR (edges whose SOURCE is local), so there is no reduce-scatter and no
+    atomics and every output row is summed in one place (deterministic);
+  * rows are never split between ranks, and a rank's CSC slice keeps the global edge order, so each
+    output row is accumulated in exactly the order the single-GPU kernel uses: P-way results are
+    bit-identical to 1-GPU results for sums, arg-max and structure.
+
+The all-gather is issued on a side stream; aggregation over local-source edges can run meanwhile
+(`overlap=True` splits the block into a local-source and a remote-source part; the two partial sums
+are added, which changes the summation order -- tolerance instead of bit-equality).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .heterograph import create_block
+from . import ops
+
+
+def balanced_row_ranges(in_degrees, world):
+    """Contiguous [lo, hi) node ranges with ~equal in-edge counts.  in_degrees: int array (N,)."""
+    n = len(in_degrees)
+    csum = np.concatenate([[0], np.cumsum(in_degrees, dtype=np.int64)])
+    total = int(csum[-1])
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r // world
+        b = int(np.searchsorted(csum, target, side="left"))
+        bounds.append(min(max(b, bounds[-1]), n))
+    bounds.append(n)
+    return [(bounds[i], bounds[i + 1]) for i in range(world)]
+
+
+class RowPartition:
+    """Per-rank view of a square graph with N nodes given by its creation-order COO (src, dst)."""
+
+    def __init__(self, n_nodes, world, rank, ranges, fwd_block, bwd_block, fwd_local=None, fwd_remote=None,
+                 n_local_edges=0, group=None):
+        self.n_nodes, self.world, self.rank, self.ranges = n_nodes, world, rank, ranges
+        self.lo, self.hi = ranges[rank]
+        self.n_local_rows = self.hi - self.lo
+        self.local_graph = fwd_block        # N global sources -> local destinations (CSC slice)
+        self.bwd_graph = bwd_block          # N global destinations -> local sources (CSR slice, reversed)
+        self.fwd_local, self.fwd_remote = fwd_local, fwd_remote
+        self.n_local_edges = n_local_edges
+        self.group = group
+        self.sizes = [hi - lo for lo, hi in ranges]
+        self._side = None
+
+    @staticmethod
+    def build(src, dst, n_nodes, world, rank, device, overlap=False, group=None):
+        src = np.asarray(src, dtype=np.int64)
+        dst = np.asarray(dst, dtype=np.int64)
+        indeg = np.bincount(dst, minlength=n_nodes)
+        ranges = balanced_row_ranges(indeg, world)
+        lo, hi = ranges[rank]
+        sel = (dst >= lo) & (dst < hi)          # keeps the global (edge-id) order of the selected edges
+        s_f, d_f = src[sel], dst[sel] - lo
+        fwd = create_block((torch.from_numpy(s_f), torch.from_numpy(d_f)), n_nodes, hi - lo).int().to(device)
+        selb = (src >= lo) & (src < hi)
+        # backward: rows = local sources, columns = global destinations; as a block: "sources" are the
+        # global dst nodes (whose dZ rows are gathered), "destinations" the local src nodes
+        bwd = create_block((torch.from_numpy(dst[selb]), torch.from_numpy(src[selb] - lo)), n_nodes, hi - lo).int().to(device)
+        fl = fr = None
+        if overlap:
+            loc = (s_f >= lo) & (s_f < hi)
+            fl = create_block((torch.from_numpy(s_f[loc] - lo), torch.from_numpy(d_f[loc])), hi - lo, hi - lo).int().to(device)
+            fr = create_block((torch.from_numpy(s_f[~loc]), torch.from_numpy(d_f[~loc])), n_nodes, hi - lo).int().to(device)
+        return RowPartition(n_nodes, world, rank, ranges, fwd, bwd, fl, fr, int(sel.sum()), group)
+
+    # ------------------------------------------------------------------ collectives
+    def all_gather_rows(self, x_local, async_op=False):
+        """Concatenate every rank's rows (ragged row counts) into the (N, ...) global tensor.
+        Equal counts: one all_gather_into_tensor.  Ragged + NCCL: grouped broadcasts straight into the
+        row slices.  Ragged + gloo (CPU tests): gather padded blocks, then copy the valid rows."""
+        x_local = x_local.contiguous()
+        out = torch.empty((self.n_nodes,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+        if self.world == 1:
+            out.copy_(x_local)
+            return (out, None) if async_op else out
+        if len(set(self.sizes)) == 1:
+            work = dist.all_gather_into_tensor(out, x_local, group=self.group, async_op=async_op)
+        elif dist.get_backend(self.group) == "nccl":
+            outs = [out[lo:hi] for lo, hi in self.ranges]
+            work = dist.all_gather(outs, x_local, group=self.group, async_op=async_op)
+        else:
+            mx = max(self.sizes)
+            pad = torch.zeros((mx,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+            pad[: x_local.shape[0]] = x_local
+            buf = [torch.empty_like(pad) for _ in range(self.world)]
+            dist.all_gather(buf, pad, group=self.group)
+            for (lo, hi), b in zip(self.ranges, buf):
+                out[lo:hi] = b[: hi - lo]
+            work = None
+        return (out, work) if async_op else out
+
+    # ------------------------------------------------------------------ partitioned ops
+    def copy_u_sum(self, x_local, reduce_op="sum"):
+        """Row-partitioned gspmm(copy_lhs, sum|mean) with autograd (all-gather fwd, all-gather bwd)."""
+        return _PartitionedCopyUSum.apply(self, x_local, reduce_op)
+
+    def u_dot_v(self, u_local, v_local):
+        """Row-partitioned gsddmm(dot) for the edges whose destination is local."""
+        u_full = self.all_gather_rows(u_local)
+        return ops.gsddmm(self.local_graph, "dot", u_full, v_local)
+
+
+class _PartitionedCopyUSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, part, x_local, reduce_op):
+        ctx.part, ctx.reduce_op = part, reduce_op
+        with torch.no_grad():
+            if part.fwd_local is not None and part.world > 1:
+                x_full, work = part.all_gather_rows(x_local, async_op=True)
+                out = ops.gspmm(part.fwd_local, "copy_lhs", "sum", x_local, None)   # overlaps the collective
+                if work is not None:
+                    work.wait()
+                out = out + ops.gspmm(part.fwd_remote, "copy_lhs", "sum", x_full, None)
+                if reduce_op == "mean":
+                    deg = part.local_graph.in_degrees().clamp(min=1).to(out.dtype)
+                    out = out / deg.view(-1, 1)
+            else:
+                x_full = part.all_gather_rows(x_local)
+                out = ops.gspmm(part.local_graph, "copy_lhs", reduce_op, x_full, None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dz_local):
+        part = ctx.part
+        with torch.no_grad():
+            dz_local = dz_local.contiguous()
+            if ctx.reduce_op == "mean":
+                deg = part.local_graph.in_degrees().clamp(min=1).to(dz_local.dtype)
+                dz_local = dz_local / deg.view(-1, 1)
+            dz_full = part.all_gather_rows(dz_local)
+            dx = ops.gspmm(part.bwd_graph, "copy_lhs", "sum", dz_full, None)
+        return None, dx, None
