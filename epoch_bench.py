@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""Full-graph epoch times (BASELINE.json metric, second half) on synthetic graphs of the reference
+datasets' shapes, 1 GPU or row-partitioned over N GPUs (torchrun).  Prints one JSON line per config.
+
+    python epoch_bench.py --configs cora_sage,arxiv_gat,reddit_sage,reddit_gat,products_sage
+    python -m torch.distributed.run --nproc-per-node 8 ... epoch_bench.py --configs products_sage
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "dgl-0.5-benchmark_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+import dgl  # noqa: E402
+from dgl import _capi  # noqa: E402
+from examples.full_graph import GAT, GraphSAGE, synthetic_task, time_epochs  # noqa: E402
+
+# name -> (dataset shape, model, kwargs, V100 seconds/epoch published in README.md:36-46)
+CONFIGS = {
+    "cora_sage": ("cora", "sage", dict(hidden=16, layers=2, aggr="mean", dropout=0.5, lr=1e-2, wd=5e-4), 0.0039),
+    "pubmed_sage": ("pubmed", "sage", dict(hidden=16, layers=2, aggr="mean", dropout=0.5, lr=1e-2, wd=5e-4), 0.0046),
+    "reddit_sage": ("reddit", "sage", dict(hidden=16, layers=2, aggr="mean", dropout=0.5, lr=1e-2, wd=5e-4), 0.3627),
+    "reddit_full_sage": ("reddit-full", "sage", dict(hidden=16, layers=2, aggr="mean", dropout=0.5, lr=1e-2, wd=5e-4), 0.3627),
+    "arxiv_sage": ("ogbn-arxiv", "sage", dict(hidden=256, layers=3, aggr="mean", dropout=0.5, lr=1e-2, wd=0, edges=2332486), 0.0943),
+    "products_sage": ("ogbn-products", "sage", dict(hidden=64, layers=3, aggr="mean", dropout=0.5, lr=1e-2, wd=0), 0.3436),
+    "products_full_sage": ("ogbn-products-full", "sage", dict(hidden=64, layers=3, aggr="mean", dropout=0.5, lr=1e-2, wd=0), 0.3436),
+    "cora_gat": ("cora", "gat", dict(hidden=8, heads=[8, 8, 1], dropout=0.6, lr=5e-3, wd=5e-4), 0.012),
+    "arxiv_gat": ("ogbn-arxiv", "gat", dict(hidden=16, heads=[4, 4, 4], dropout=0.18074706609292976,
+                                            lr=0.0029739421726400865, wd=2.4222556964495987e-05, edges=2315598), 0.0798),
+    "reddit_gat": ("reddit", "gat", dict(hidden=16, heads=[1, 1, 1], dropout=0.18074706609292976,
+                                         lr=0.0029739421726400865, wd=2.4222556964495987e-05), 0.5532),
+    "reddit_full_gat": ("reddit-full", "gat", dict(hidden=16, heads=[1, 1, 1], dropout=0.18074706609292976,
+                                                   lr=0.0029739421726400865, wd=2.4222556964495987e-05), 0.5532),
+}
+
+
+def run_config(name, epochs, rank, world, dev, degree, unfused=False):
+    shape, kind, kw, v100 = CONFIGS[name]
+    (n, src, dst), feats, labels, train_idx, n_classes = synthetic_task(
+        shape, dev, degree=degree, self_loops=(kind == "gat"), edges=kw.get("edges"))
+    n_edges = len(src)
+    if world > 1:
+        if kind != "sage":
+            raise SystemExit("row-partitioned training is implemented for the SAGE configs")
+        from dgl.distributed_rows import RowPartition
+        part = RowPartition.build(src, dst, n, world, rank, dev)
+        graph = part
+        lo, hi = part.lo, part.hi
+        feats, labels = feats[lo:hi].to(dev), labels[lo:hi].to(dev)
+        tmask = torch.zeros(n, dtype=torch.bool)
+        tmask[train_idx] = True
+        train_idx = torch.nonzero(tmask[lo:hi]).view(-1).to(dev)
+        n_train_total = int(tmask.sum())
+    else:
+        graph = dgl.graph((torch.from_numpy(src), torch.from_numpy(dst)), num_nodes=n).int().to(dev)
+        feats, labels, train_idx = feats.to(dev), labels.to(dev), train_idx.to(dev)
+        n_train_total = train_idx.numel()
+    torch.manual_seed(0)
+    if kind == "sage":
+        model = GraphSAGE(feats.shape[1], kw["hidden"], n_classes, kw["layers"], kw["aggr"], kw["dropout"]).to(dev)
+    else:
+        from dgl.nn.pytorch import GATConv
+        GATConv.fused = not unfused
+        model = GAT(feats.shape[1], kw["hidden"], n_classes, kw["heads"], kw["dropout"], kw["dropout"]).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=kw["lr"], weight_decay=kw["wd"])
+    losses = []
+
+    def step():
+        model.train()
+        opt.zero_grad()
+        out = model(graph, feats)
+        if kind == "sage":
+            loss = F.cross_entropy(out[train_idx], labels[train_idx], reduction="sum") / n_train_total
+        else:
+            loss = F.nll_loss(out[train_idx], labels[train_idx])
+        loss.backward()
+        if world > 1:
+            for p in model.parameters():
+                dist.all_reduce(p.grad)
+        opt.step()
+        losses.append(loss.item())       # synchronises, like the OGB scripts (main_dgl_arxiv_gat.py:74)
+
+    l0 = _capi.launches()
+    mean_s, dur = time_epochs(step, epochs)
+    launches = (_capi.launches() - l0) / epochs
+    if world > 1:
+        t = torch.tensor([mean_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        mean_s = float(t.item())
+    return {"config": name, "dataset_shape": shape, "nodes": n, "edges": n_edges, "model": kind, "n_gpus": world,
+            "epoch_s": mean_s, "epoch_s_min": float(np.min(dur)), "epochs_timed": len(dur),
+            "v100_dgl_epoch_s_published": v100, "sparse_launches_per_epoch": launches,
+            "loss_first": losses[0], "loss_last": losses[-1], "degree": degree,
+            "gat_fused": (kind == "gat" and not unfused), "data": "synthetic"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="cora_sage,arxiv_gat,reddit_sage,reddit_gat,products_sage")
+    ap.add_argument("--epochs", type=int, default=13)
+    ap.add_argument("--degree", default="uniform", choices=["uniform", "powerlaw"])
+    ap.add_argument("--unfused", action="store_true", help="GATConv op-by-op composition instead of the fused kernels")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    for name in args.configs.split(","):
+        res = run_config(name, args.epochs, rank, world, dev, args.degree, args.unfused)
+        if rank == 0:
+            print(json.dumps(res), flush=True)
+        torch.cuda.empty_cache()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,112 @@
+"""Full-graph GraphSAGE / GAT training on synthetic graphs of the reference datasets' shapes, written
+against the drop-in `dgl` package.  The models restate the reference scripts' architectures and
+hyper-parameters (main_dgl_citation_sage.py:20-120, main_dgl_product_sage.py:33-100,
+main_dgl_arxiv_gat.py:14-63, main_dgl_reddit_gat.py) so epoch times are comparable in shape with
+README.md:36-46; the epoch timer follows the scripts (skip the first 3 epochs) but always
+synchronises the device.  With a RowPartition the SAGE model trains row-partitioned on N GPUs
+(all-gather of the layer input forward, of the output gradient backward; dense grads all-reduced).
+"""
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+import dgl
+import dgl.function as fn
+from dgl.data import synthetic
+from dgl.nn.pytorch import GATConv
+
+
+class SAGELayer(nn.Module):
+    """h' = W_self h + W_neigh aggregate(h)  (aggregate BEFORE the projection, as the hand-written
+    layer of main_dgl_citation_sage.py:44-86 does)."""
+
+    def __init__(self, in_feats, out_feats, aggr="mean", feat_drop=0.0, activation=None):
+        super().__init__()
+        self.aggr, self.activation = aggr, activation
+        self.feat_drop = nn.Dropout(feat_drop)
+        self.fc_self = nn.Linear(in_feats, out_feats, bias=False)
+        self.fc_neigh = nn.Linear(in_feats, out_feats)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        gain = nn.init.calculate_gain("relu")
+        nn.init.xavier_uniform_(self.fc_self.weight, gain=gain)
+        nn.init.xavier_uniform_(self.fc_neigh.weight, gain=gain)
+
+    def forward(self, graph, feat):
+        h = self.feat_drop(feat)
+        if hasattr(graph, "copy_u_sum"):          # RowPartition: collective + local kernel
+            h_neigh = graph.copy_u_sum(h, self.aggr)
+        else:
+            g = graph.local_var()
+            g.srcdata["h"] = h
+            g.update_all(fn.copy_src("h", "m"), fn.mean("m", "neigh") if self.aggr == "mean" else fn.sum("m", "neigh"))
+            h_neigh = g.dstdata["neigh"]
+        rst = self.fc_self(h) + self.fc_neigh(h_neigh)
+        return self.activation(rst) if self.activation is not None else rst
+
+
+class GraphSAGE(nn.Module):
+    def __init__(self, in_feats, n_hidden, n_classes, n_layers=2, aggr="mean", dropout=0.5):
+        super().__init__()
+        dims = [in_feats] + [n_hidden] * (n_layers - 1) + [n_classes]
+        self.layers = nn.ModuleList(
+            SAGELayer(dims[i], dims[i + 1], aggr, feat_drop=(dropout if i > 0 else 0.0),
+                      activation=(F.relu if i < n_layers - 1 else None)) for i in range(n_layers))
+
+    def forward(self, graph, h):
+        for layer in self.layers:
+            h = layer(graph, h)
+        return h
+
+
+class GAT(nn.Module):
+    """3-layer GAT of main_dgl_arxiv_gat.py:14-63 (heads e.g. [4,4,4]; hidden layers flatten heads,
+    the last layer averages them; log-softmax output)."""
+
+    def __init__(self, in_feats, n_hidden, n_classes, heads, feat_drop=0.0, attn_drop=0.0, negative_slope=0.2):
+        super().__init__()
+        n = len(heads)
+        self.layers = nn.ModuleList()
+        self.layers.append(GATConv(in_feats, n_hidden, heads[0], 0.0, 0.0, negative_slope, activation=F.elu))
+        for l in range(n - 2):
+            self.layers.append(GATConv(n_hidden * heads[l], n_hidden, heads[l + 1], feat_drop, attn_drop,
+                                       negative_slope, activation=F.elu))
+        self.layers.append(GATConv(n_hidden * heads[-2], n_classes, heads[-1], feat_drop, attn_drop, negative_slope))
+
+    def forward(self, g, h):
+        for layer in self.layers[:-1]:
+            h = layer(g, h).flatten(1)
+        return self.layers[-1](g, h).mean(1).log_softmax(dim=-1)
+
+
+def synthetic_task(name, device, seed=0, degree="uniform", self_loops=False, edges=None):
+    """(graph on device, features, labels, train index) with the shape of dataset `name`."""
+    n, e, d, c = synthetic.SHAPES[name]
+    if edges is not None:
+        e = edges
+    src, dst = synthetic.random_edges(n, n, e, seed=seed, degree=degree)
+    if self_loops:
+        loops = np.arange(n)
+        src, dst = np.concatenate([src, loops]), np.concatenate([dst, loops])
+    gen = torch.Generator().manual_seed(seed)
+    feats = torch.rand(n, d, generator=gen)
+    labels = torch.randint(0, c, (n,), generator=gen)
+    train_idx = torch.randperm(n, generator=gen)[: max(1, n // 10)]
+    return (n, src, dst), feats, labels, train_idx, c
+
+
+def time_epochs(step, epochs, skip=3):
+    """Mean wall time of step() over epochs after `skip` warm-up epochs (device synchronised)."""
+    dur = []
+    for ep in range(epochs):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step()
+        torch.cuda.synchronize()
+        if ep >= skip:
+            dur.append(time.perf_counter() - t0)
+    return float(np.mean(dur)), dur
