@@ -243,6 +243,7 @@ int dglb_gat_fused_fwd(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz, int
   p.indptr = indptr; p.indices = indices; p.eids = eids;
   p.ft = static_cast<const float*>(ft); p.el = static_cast<const float*>(el); p.er = static_cast<const float*>(er);
   p.out_feat = static_cast<float*>(rst); p.out_h0 = row_max; p.out_h1 = row_sum;
+  p.row_max = row_max; p.row_sum = row_sum;
   p.edge_scores = static_cast<float*>(edge_scores); p.hub_rows = hub_rows; p.n_rows = n_dst; p.slope = negative_slope;
   return gat_fused_f32(0, p, n_heads, head_dim, dropout_p, seed, n_hub, hub_threshold, static_cast<cudaStream_t>(stream));
 }
@@ -251,39 +252,40 @@ int dglb_gat_fused_bwd_dst(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz,
                            float negative_slope, float dropout_p, uint64_t seed, const int32_t* indptr,
                            const int32_t* indices, const int32_t* eids, const void* ft, const void* el,
                            const void* er, const float* row_max, const float* row_sum, const void* grad_rst,
-                           float* s1, void* grad_er, const int32_t* hub_rows, int32_t n_hub,
+                           float* row_pack, void* grad_er, const int32_t* hub_rows, int32_t n_hub,
                            int32_t hub_threshold, void* stream) {
   (void)n_src;
   if (dtype != DGLB_F32) { set_error("gat_fused: only f32 is implemented"); return DGLB_E_UNSUPPORTED; }
   DGLB_CHECK_ARG(n_dst >= 0 && nnz >= 0 && indptr && (indices || nnz == 0), "gat_fused_bwd_dst: bad graph");
-  DGLB_CHECK_ARG(n_dst == 0 || (er && row_max && row_sum && grad_rst && s1 && grad_er), "gat_fused_bwd_dst: null data");
+  DGLB_CHECK_ARG(n_dst == 0 || (er && row_max && row_sum && grad_rst && row_pack && grad_er), "gat_fused_bwd_dst: null data");
   DGLB_CHECK_ARG((ft && el) || nnz == 0, "gat_fused_bwd_dst: null ft/el");
+  DGLB_CHECK_ARG((reinterpret_cast<uintptr_t>(row_pack) & 15) == 0, "gat_fused_bwd_dst: row_pack must be 16-byte aligned");
   GatParams p;
   gat_zero(p);
   p.indptr = indptr; p.indices = indices; p.eids = eids;
   p.ft = static_cast<const float*>(ft); p.el = static_cast<const float*>(el); p.er = static_cast<const float*>(er);
   p.row_max = row_max; p.row_sum = row_sum; p.dZ = static_cast<const float*>(grad_rst);
-  p.out_h0 = s1; p.out_h1 = static_cast<float*>(grad_er); p.hub_rows = hub_rows; p.n_rows = n_dst;
-  p.slope = negative_slope;
+  p.out_pack = reinterpret_cast<float4*>(row_pack); p.out_h0 = static_cast<float*>(grad_er); p.hub_rows = hub_rows;
+  p.n_rows = n_dst; p.slope = negative_slope;
   return gat_fused_f32(1, p, n_heads, head_dim, dropout_p, seed, n_hub, hub_threshold, static_cast<cudaStream_t>(stream));
 }
 
 int dglb_gat_fused_bwd_src(int dtype, int64_t n_src, int64_t n_dst, int64_t nnz, int64_t n_heads, int64_t head_dim,
                            float negative_slope, float dropout_p, uint64_t seed, const int32_t* indptr_csr,
                            const int32_t* indices_csr, const int32_t* eids_csr, const void* ft, const void* el,
-                           const void* er, const float* row_max, const float* row_sum, const float* s1,
-                           const void* grad_rst, void* grad_ft, void* grad_el, const int32_t* hub_rows,
-                           int32_t n_hub, int32_t hub_threshold, void* stream) {
+                           const float* row_pack, const void* grad_rst, void* grad_ft, void* grad_el,
+                           const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold, void* stream) {
   (void)n_dst;
   if (dtype != DGLB_F32) { set_error("gat_fused: only f32 is implemented"); return DGLB_E_UNSUPPORTED; }
   DGLB_CHECK_ARG(n_src >= 0 && nnz >= 0 && indptr_csr && (indices_csr || nnz == 0), "gat_fused_bwd_src: bad graph");
   DGLB_CHECK_ARG(n_src == 0 || (ft && el && grad_ft && grad_el), "gat_fused_bwd_src: null src data");
-  DGLB_CHECK_ARG(nnz == 0 || (er && row_max && row_sum && s1 && grad_rst), "gat_fused_bwd_src: null dst data");
+  DGLB_CHECK_ARG(nnz == 0 || (row_pack && grad_rst), "gat_fused_bwd_src: null dst data");
+  DGLB_CHECK_ARG((reinterpret_cast<uintptr_t>(row_pack) & 15) == 0, "gat_fused_bwd_src: row_pack must be 16-byte aligned");
   GatParams p;
   gat_zero(p);
   p.indptr = indptr_csr; p.indices = indices_csr; p.eids = eids_csr;
-  p.ft = static_cast<const float*>(ft); p.el = static_cast<const float*>(el); p.er = static_cast<const float*>(er);
-  p.row_max = row_max; p.row_sum = row_sum; p.s1 = s1; p.dZ = static_cast<const float*>(grad_rst);
+  p.ft = static_cast<const float*>(ft); p.el = static_cast<const float*>(el);
+  p.pack = reinterpret_cast<const float4*>(row_pack); p.dZ = static_cast<const float*>(grad_rst);
   p.out_feat = static_cast<float*>(grad_ft); p.out_h0 = static_cast<float*>(grad_el); p.hub_rows = hub_rows;
   p.n_rows = n_src; p.slope = negative_slope;
   return gat_fused_f32(2, p, n_heads, head_dim, dropout_p, seed, n_hub, hub_threshold, static_cast<cudaStream_t>(stream));

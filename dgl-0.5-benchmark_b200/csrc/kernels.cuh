@@ -28,19 +28,21 @@ struct GatParams {
   const float* __restrict__ ft;         // (n_src, H, F)
   const float* __restrict__ el;         // (n_src, H)
   const float* __restrict__ er;         // (n_dst, H)
-  const float* __restrict__ row_max;    // (n_dst, H)   (fwd: written)
-  const float* __restrict__ row_sum;
-  const float* __restrict__ s1;         // (n_dst, H)   (bwd_src: read)
+  const float* __restrict__ row_max;    // (n_dst, H)
+  const float* __restrict__ row_sum;    // (n_dst, H)
+  const float4* __restrict__ pack;      // (n_dst, H) {er, max, sum, s1}   (bwd_src: read)
   const float* __restrict__ dZ;         // (n_dst, H, F) grad of rst
   float* __restrict__ out_feat;         // fwd: rst (n_dst,H,F); bwd_src: grad_ft (n_src,H,F)
-  float* __restrict__ out_h0;           // fwd: row_max; bwd_dst: s1;      bwd_src: grad_el
-  float* __restrict__ out_h1;           // fwd: row_sum; bwd_dst: grad_er
+  float* __restrict__ out_h0;           // rowstats: row_max; bwd_dst: grad_er; bwd_src: grad_el
+  float* __restrict__ out_h1;           // rowstats: row_sum
+  float4* __restrict__ out_pack;        // bwd_dst: (n_dst, H) {er, max, sum, s1}
   float* __restrict__ edge_scores;      // fwd only, may be null
   const int32_t* __restrict__ hub_rows;
   int64_t n_rows;
   int H, F, D;  // D = H*F
   int ncols;    // D / VEC
   int G, log2G;
+  int HP, log2HP;  // rowstats: heads padded to a power of two (lanes per edge)
   int hub_threshold;
   float slope;
   float drop_p, drop_scale;  // drop_scale = 1/(1-p)

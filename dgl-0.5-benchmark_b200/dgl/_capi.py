@@ -53,7 +53,7 @@ _SIGNATURES = {
     "dglb_gat_fused_bwd_dst": (_int, [_int, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _u64, _vp, _vp, _vp,
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "dglb_gat_fused_bwd_src": (_int, [_int, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _u64, _vp, _vp, _vp,
-                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
 }
 
 

@@ -281,7 +281,7 @@ def _gat_fwd(gidx, ft, el, er, slope, dropout_p, seed, want_scores=False):
                               _capi.ptr(ft), _capi.ptr(el), _capi.ptr(er), _capi.ptr(rst), _capi.ptr(row_max),
                               _capi.ptr(row_sum), _capi.ptr(scores), _capi.ptr(hub_rows), n_hub, thr, stream)
     _capi.check(rc, "dglb_gat_fused_fwd")
-    _capi.count_launch(1 + (1 if n_hub else 0))
+    _capi.count_launch(2 + (2 if n_hub else 0))   # row statistics + weighted gather
     return rst, row_max, row_sum, scores
 
 
@@ -291,7 +291,7 @@ def _gat_bwd(gidx, ft, el, er, row_max, row_sum, grad_rst, slope, dropout_p, see
     grad_rst = grad_rst.contiguous()
     H, F = ft.shape[1], ft.shape[2]
     csc, csr = gidx.csc(), gidx.csr()
-    s1 = torch.empty((gidx.n_dst, H), dtype=torch.float32, device=dev)
+    row_pack = torch.empty((gidx.n_dst, H, 4), dtype=torch.float32, device=dev)  # {er, max, sum, s1}
     grad_er = torch.empty((gidx.n_dst, H), dtype=ft.dtype, device=dev)
     grad_ft = torch.empty_like(ft)
     grad_el = torch.empty((gidx.n_src, H), dtype=ft.dtype, device=dev)
@@ -303,7 +303,7 @@ def _gat_bwd(gidx, ft, el, er, row_max, row_sum, grad_rst, slope, dropout_p, see
         rc = l.dglb_gat_fused_bwd_dst(_capi.F32, csc.n_rows, csc.n_cols, csc.nnz, H, F, float(slope),
                                       float(dropout_p), int(seed), _capi.ptr(csc.indptr), _capi.ptr(csc.indices),
                                       _capi.ptr(csc.eids), _capi.ptr(ft), _capi.ptr(el), _capi.ptr(er),
-                                      _capi.ptr(row_max), _capi.ptr(row_sum), _capi.ptr(grad_rst), _capi.ptr(s1),
+                                      _capi.ptr(row_max), _capi.ptr(row_sum), _capi.ptr(grad_rst), _capi.ptr(row_pack),
                                       _capi.ptr(grad_er), _capi.ptr(hub_rows), n_hub, thr, stream)
         _capi.check(rc, "dglb_gat_fused_bwd_dst")
         _capi.count_launch(1 + (1 if n_hub else 0))
@@ -311,9 +311,9 @@ def _gat_bwd(gidx, ft, el, er, row_max, row_sum, grad_rst, slope, dropout_p, see
         hub_rows, n_hub = csr.hubs(thr)
         rc = l.dglb_gat_fused_bwd_src(_capi.F32, csr.n_rows, csr.n_cols, csr.nnz, H, F, float(slope),
                                       float(dropout_p), int(seed), _capi.ptr(csr.indptr), _capi.ptr(csr.indices),
-                                      _capi.ptr(csr.eids), _capi.ptr(ft), _capi.ptr(el), _capi.ptr(er),
-                                      _capi.ptr(row_max), _capi.ptr(row_sum), _capi.ptr(s1), _capi.ptr(grad_rst),
-                                      _capi.ptr(grad_ft), _capi.ptr(grad_el), _capi.ptr(hub_rows), n_hub, thr, stream)
+                                      _capi.ptr(csr.eids), _capi.ptr(ft), _capi.ptr(el), _capi.ptr(row_pack),
+                                      _capi.ptr(grad_rst), _capi.ptr(grad_ft), _capi.ptr(grad_el),
+                                      _capi.ptr(hub_rows), n_hub, thr, stream)
         _capi.check(rc, "dglb_gat_fused_bwd_src")
         _capi.count_launch(1 + (1 if n_hub else 0))
     return grad_ft, grad_el, grad_er

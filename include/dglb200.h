@@ -199,7 +199,9 @@ int dglb_edge_softmax_bwd(int dtype, int64_t n_dst, int64_t nnz, int64_t n_heads
  * attention-dropout factor (0 or 1/(1-p)) derived from a counter-based hash of
  * (seed, edge id, head), so the backward regenerates it; dropout_p = 0 disables it.
  * Backward is two kernels that recompute the scores (dd_j = drop_j * ft[src_j,h,:].grad_rst[v,h,:]):
- *   _bwd_dst (CSC over dst): s1[v,h] = sum_j a_j*dd_j ; grad_er[v,h] = sum_j a_j*(dd_j - s1)*lrelu'_j
+ *   _bwd_dst (CSC over dst): s1[v,h] = sum_j a_j*dd_j ; grad_er[v,h] = sum_j a_j*(dd_j - s1)*lrelu'_j ;
+ *                            also writes row_pack[v,h] = {er, row_max, row_sum, s1} (one 16-byte record
+ *                            per (node, head) so the src pass fetches it with a single load per edge)
  *   _bwd_src (CSR over src): grad_ft[u,h,:] = sum_{u->v} a*drop*grad_rst[v,h,:] ;
  *                            grad_el[u,h]   = sum_{u->v} a*(dd - s1[v,h])*lrelu'
  * optional `edge_scores` (E,H) in edge-id order receives a_j (before dropout); pass NULL on the
@@ -222,7 +224,7 @@ int dglb_gat_fused_bwd_dst(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz,
                            const void* ft, const void* el, const void* er,
                            const float* row_max, const float* row_sum,
                            const void* grad_rst,
-                           float* s1 /* (n_dst,H) */, void* grad_er /* (n_dst,H) */,
+                           float* row_pack /* (n_dst,H,4), 16-byte aligned */, void* grad_er /* (n_dst,H) */,
                            const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
                            void* stream);
 
@@ -231,8 +233,8 @@ int dglb_gat_fused_bwd_src(int dtype, int64_t n_src, int64_t n_dst, int64_t nnz,
                            float dropout_p, uint64_t seed,
                            const int32_t* indptr_csr, const int32_t* indices_csr /* dst ids */,
                            const int32_t* eids_csr,
-                           const void* ft, const void* el, const void* er,
-                           const float* row_max, const float* row_sum, const float* s1,
+                           const void* ft, const void* el,
+                           const float* row_pack /* from _bwd_dst */,
                            const void* grad_rst,
                            void* grad_ft /* (n_src,H,F) */, void* grad_el /* (n_src,H) */,
                            const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
