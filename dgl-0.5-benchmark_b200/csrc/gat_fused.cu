@@ -212,7 +212,7 @@ __device__ __forceinline__ void store_feat_tile(const GatParams& p, float (&acc)
 
 // ------------------------------------------------------------------ forward 2/2: weighted gather
 template <int VEC, int CH, bool HUB>
-__global__ void __launch_bounds__(kBlockThreads, 3) gat_fwd_kernel(const GatParams p) {
+__global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatParams p) {
   constexpr int U = 8 / CH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_val = reinterpret_cast<float*>(smem_raw);
