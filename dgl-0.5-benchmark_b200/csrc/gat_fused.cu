@@ -5,26 +5,27 @@
 // main_pyg_arxiv_gat.py:98-111), upstream DGL v0.6.1's chain of ~7 sparse + 3 elementwise
 // launches forward and ~6 + 5 backward and its per-edge (E,H) intermediates.
 //
-// Forward = two launches, nothing per-edge is ever written:
-//   1. gat_rowstats_kernel (CSC; a warp per destination row, lanes = (edge slot, head)):
-//      e = lrelu(el[src] + er[v]); row_max[v,h] = max e; row_sum[v,h] = sum exp(e - max)
-//      -- the same formula as upstream's edge_softmax.  Traffic: 4 + 4H bytes per edge.
-//   2. gat_fwd_kernel: the SpMM row-per-group gather in which EVERY LANE recomputes the weight
-//      of its own head,  a = exp(lrelu(el[src,h] + er[v,h]) - max[v,h]) / sum[v,h]  (x dropout),
-//      from one extra 4-byte load per chunk.  The redundant exp per lane is free on a gather-bound
-//      kernel, and it removes every cross-lane dependency from the inner loop: the source row and
-//      its el value are fetched by independent loads issued back to back (U*CH in flight), exactly
-//      like gspmm u_mul_e.  (Round-1 profile: the first version, whose owner lane computed the
-//      weights and broadcast them with H shuffles per edge after in-kernel reductions, ran 2x
-//      slower than plain u_mul_e_sum -- profiles/r01_notes.md.)
-// Backward = two launches that RECOMPUTE a_j per lane the same way:
-//   gat_bwd_kernel<SRC_PASS=false> (CSC): per-lane partials of  S1 = sum_j a_j dd_j  and
-//      S2 = sum_j a_j g_j dd_j  (dd_j = drop_j <ft[src_j,h,:], dZ[v,h,:]>, g = lrelu') are
-//      accumulated over the row's edges and reduced across lanes ONCE per row (the sums are linear
-//      in the per-lane partial dots); S3 = sum_j a_j g_j;  grad_er = S2 - S1*S3;  writes the 16-byte
+// All three kernels share one scheme (a group of G lanes per row, as in spmm.cu):
+//   * "owner" phase, once per batch of G edges: lane j loads the neighbour id of edge j and the H
+//     per-head scalars it needs (el[src,:] forward / dst pass, the 16-byte destination record in the
+//     src pass), computes the attention weight(s) of ITS edge -- one exp and one divide per
+//     (edge, head), no redundancy -- and parks them in shared memory;
+//   * gather phase: every lane streams its 128-bit chunks of the neighbour rows (U*CH independent
+//     loads in flight) and picks the weight of its own head with ONE shared-memory load per chunk
+//     (a broadcast read: no shuffles, no select chains, no per-lane exp).
+//   Round-1 history (profiles/r01_notes.md): v1 broadcast the weights with H shuffles + CH*H selects
+//   per edge, v2 recomputed exp/div in every lane; both were instruction-bound at 2x the time of a
+//   plain u_mul_e_sum.  This version issues ~3x fewer instructions per edge.
+// Forward (CSC): per-head max and sum of exp are reduced inside the kernel (group shuffles; rows of
+//   <= G edges keep their logits in registers), following upstream's edge_softmax formula
+//   exp(e - max) / sum; row_max / row_sum (N,H) are saved; nothing per-edge is written.
+// Backward, scores recomputed from (el, er, row_max, row_sum):
+//   dst pass (CSC): per-lane partials of S1 = sum_j a_j dd_j and S2 = sum_j a_j g_j dd_j
+//      (dd_j = drop_j <ft[src_j,h,:], dZ[v,h,:]>, g = lrelu') are accumulated over the row's edges
+//      and reduced across lanes ONCE per row (the sums are linear in the per-lane partial dots);
+//      S3 = sum_j a_j g_j comes from the owner lanes;  grad_er = S2 - S1*S3;  writes the 16-byte
 //      record row_pack[v,h] = {er, max, sum, S1}.
-//   gat_bwd_kernel<SRC_PASS=true> (CSR): grad_ft[u] = sum a*drop*dZ[v];
-//      grad_el[u] = sum a g (dd - S1[v]); the destination's record is one LDG.128 per edge.
+//   src pass (CSR): grad_ft[u] = sum a*drop*dZ[v];  grad_el[u] = sum a g (dd - S1[v]).
 // Hub rows: one CTA per row; the groups split the edges and meet in shared memory.
 #include "kernels.cuh"
 
@@ -100,79 +101,33 @@ __device__ __forceinline__ void gat_group_work(const GatParams& p, int64_t& row,
   }
 }
 
-// ------------------------------------------------------------------ forward 1/2: row statistics
-__device__ __forceinline__ float slot_max(float v, int HP) {
-  for (int s = 16; s >= HP; s >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, s));
-  return v;
-}
-__device__ __forceinline__ float slot_sum(float v, int HP) {
-  for (int s = 16; s >= HP; s >>= 1) v += __shfl_xor_sync(FULL_MASK, v, s);
-  return v;
-}
-template <bool IS_MAX>
-__device__ __forceinline__ float cta_slot_reduce(float v, float* s_buf /* [8][32] */) {
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();
-  s_buf[w * 32 + lane] = v;
-  __syncthreads();
-  float r = s_buf[lane];
+// ------------------------------------------------------------------ shared helpers
+template <int HT>
+__device__ __forceinline__ void group_allreduce_max(float (&v)[HT], int G) {
 #pragma unroll
-  for (int i = 1; i < kBlockThreads / 32; ++i) {
-    const float o = s_buf[i * 32 + lane];
-    r = IS_MAX ? fmaxf(r, o) : r + o;
+  for (int h = 0; h < HT; ++h)
+    for (int s = G >> 1; s > 0; s >>= 1) v[h] = fmaxf(v[h], __shfl_xor_sync(FULL_MASK, v[h], s));
+}
+template <int HT>
+__device__ __forceinline__ void cta_allreduce_max(float (&v)[HT], float* s_buf, int gidx, int lg, int n_groups) {
+  __syncthreads();
+  if (lg == 0) {
+#pragma unroll
+    for (int h = 0; h < HT; ++h) s_buf[gidx * HT + h] = v[h];
   }
-  return r;
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < HT; ++h) {
+    float r = s_buf[h];
+    for (int g = 1; g < n_groups; ++g) r = fmaxf(r, s_buf[g * HT + h]);
+    v[h] = r;
+  }
 }
 
-template <bool HUB>
-__global__ void __launch_bounds__(kBlockThreads) gat_rowstats_kernel(const GatParams p) {
-  __shared__ float s_buf[HUB ? kBlockThreads : 1];
-  const int lane = threadIdx.x & 31;
-  const int h = lane & (p.HP - 1);
-  const bool hv = h < p.H;
-  int64_t row;
-  int start = 0, deg = 0, slot, nslots;
-  bool write;
-  if constexpr (!HUB) {
-    row = ((int64_t)blockIdx.x * kBlockThreads + threadIdx.x) >> 5;
-    write = row < p.n_rows;
-    if (write) {
-      start = __ldg(p.indptr + row);
-      deg = __ldg(p.indptr + row + 1) - start;
-      if (deg > p.hub_threshold) { deg = 0; write = false; }
-    } else {
-      row = 0;
-    }
-    slot = lane >> p.log2HP;
-    nslots = 32 >> p.log2HP;
-  } else {
-    row = p.hub_rows[blockIdx.x];
-    write = true;
-    start = __ldg(p.indptr + row);
-    deg = __ldg(p.indptr + row + 1) - start;
-    slot = threadIdx.x >> p.log2HP;
-    nslots = kBlockThreads >> p.log2HP;
-  }
-  const float er = (hv && write) ? __ldg(p.er + row * p.H + h) : 0.f;
-  float mx = -INFINITY;
-  for (int i = slot; i < deg; i += nslots) {
-    const int c = __ldg(p.indices + start + i);
-    if (hv) mx = fmaxf(mx, lrelu(__fadd_rn(__ldg(p.el + (int64_t)c * p.H + h), er), p.slope));
-  }
-  mx = slot_max(mx, p.HP);
-  if constexpr (HUB) mx = cta_slot_reduce<true>(mx, s_buf);
-  float sum = 0.f;
-  for (int i = slot; i < deg; i += nslots) {
-    const int c = __ldg(p.indices + start + i);
-    if (hv) sum += expf(__fsub_rn(lrelu(__fadd_rn(__ldg(p.el + (int64_t)c * p.H + h), er), p.slope), mx));
-  }
-  sum = slot_sum(sum, p.HP);
-  if constexpr (HUB) sum = cta_slot_reduce<false>(sum, s_buf);
-  if (write && hv && slot == 0) {
-    p.out_h0[row * p.H + h] = mx;
-    p.out_h1[row * p.H + h] = sum;
-  }
-}
+// stride (in floats) between the weight slots of consecutive groups: the +HT skews the groups of a
+// warp onto different banks
+template <int HT, int NW>
+__device__ __forceinline__ int group_stride(int G) { return (G * HT + (G >= 8 ? HT : 0)) * NW; }
 
 // shared epilogue: write a feature tile (row kernel) or combine the CTA's groups (hub kernel)
 template <int VEC, int CH, bool HUB>
@@ -210,12 +165,13 @@ __device__ __forceinline__ void store_feat_tile(const GatParams& p, float (&acc)
   }
 }
 
-// ------------------------------------------------------------------ forward 2/2: weighted gather
-template <int VEC, int CH, bool HUB>
+// ------------------------------------------------------------------ forward
+template <int VEC, int CH, int HT, bool HUB>
 __global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatParams p) {
   constexpr int U = 8 / CH;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* s_val = reinterpret_cast<float*>(smem_raw);
+  __shared__ __align__(16) float s_w[(kBlockThreads + 32) * HT];  // [group][edge slot][head] weights
+  extern __shared__ __align__(16) unsigned char smem_raw[];       // hub rows only
+  float* s_buf = reinterpret_cast<float*>(smem_raw);
   const int G = p.G, H = p.H;
   const int lg = threadIdx.x & (G - 1);
   int64_t row, j0;
@@ -223,54 +179,100 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatPara
   int n, gidx, n_groups;
   gat_group_work<HUB>(p, row, active, j0, n, gidx, n_groups);
   const int nmax = __reduce_max_sync(FULL_MASK, n);
+  const bool single = nmax <= G;  // every row of this warp fits one batch: logits stay in registers
   const bool live = active || HUB;
   const bool need_e = p.drop_p > 0.f || p.edge_scores != nullptr;
+  float* my_w = s_w + gidx * group_stride<HT, 1>(G);
 
+  float er_h[HT], mx[HT], sm[HT], e_reg[HT];
+#pragma unroll
+  for (int h = 0; h < HT; ++h) {
+    er_h[h] = (h < H && live) ? __ldg(p.er + row * H + h) : 0.f;
+    mx[h] = -INFINITY; sm[h] = 0.f; e_reg[h] = -INFINITY;
+  }
+  // ---- statistics 1: per-head max of the logits
+  for (int off = 0; off < nmax; off += G) {
+    const bool valid = off + lg < n;
+    const int c = valid ? __ldg(p.indices + j0 + off + lg) : 0;
+#pragma unroll
+    for (int h = 0; h < HT; ++h) {
+      const float e = (valid && h < H) ? lrelu(__fadd_rn(__ldg(p.el + (int64_t)c * H + h), er_h[h]), p.slope)
+                                       : -INFINITY;
+      e_reg[h] = e;
+      mx[h] = fmaxf(mx[h], e);
+    }
+  }
+  group_allreduce_max<HT>(mx, G);
+  if constexpr (HUB) cta_allreduce_max<HT>(mx, s_buf, gidx, lg, n_groups);
+  // ---- statistics 2: per-head sum of exp(e - max)
+  for (int off = 0; off < nmax; off += G) {
+    const bool valid = off + lg < n;
+    const int c = (valid && !single) ? __ldg(p.indices + j0 + off + lg) : 0;
+#pragma unroll
+    for (int h = 0; h < HT; ++h) {
+      if (valid && h < H) {
+        const float e = single ? e_reg[h]
+                               : lrelu(__fadd_rn(__ldg(p.el + (int64_t)c * H + h), er_h[h]), p.slope);
+        sm[h] += expf(__fsub_rn(e, mx[h]));
+      }
+    }
+  }
+  group_allreduce_sum<HT>(sm, G);
+  if constexpr (HUB) cta_allreduce_sum<HT>(sm, s_buf, gidx, lg, n_groups);
+  if (active && lg < H && (!HUB || gidx == 0)) {
+#pragma unroll
+    for (int h = 0; h < HT; ++h)
+      if (h == lg) { p.out_h0[row * H + h] = mx[h]; p.out_h1[row * H + h] = sm[h]; }
+  }
+
+  // ---- weighted gather of the source rows
   for (int tile0 = 0; tile0 < p.ncols; tile0 += G * CH) {
     float acc[CH][VEC];
     bool colv[CH];
     int k[CH], hk[CH];
-    float er_c[CH], mx_c[CH], sm_c[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int vc = tile0 + c * G + lg;
       colv[c] = vc < p.ncols;
       k[c] = vc * VEC;
       hk[c] = colv[c] ? k[c] / p.F : 0;
-      er_c[c] = 0.f; mx_c[c] = 0.f; sm_c[c] = 1.f;
-      if (live && colv[c]) {
-        er_c[c] = __ldg(p.er + row * H + hk[c]);
-        mx_c[c] = __ldg(p.row_max + row * H + hk[c]);
-        sm_c[c] = __ldg(p.row_sum + row * H + hk[c]);
-      }
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[c][v] = 0.f;
     }
     for (int off = 0; off < nmax; off += G) {
       const int m = min(max(n - off, 0), G);
-      int my_c = 0, my_e = 0;
+      // owner phase: lane lg computes the weights of edge off+lg and parks them in shared memory
+      int my_c = 0;
       if (lg < m) {
         my_c = __ldg(p.indices + j0 + off + lg);
-        if (need_e) my_e = p.eids ? __ldg(p.eids + j0 + off + lg) : (int)(j0 + off + lg);
+        const int64_t my_e = need_e ? (p.eids ? (int64_t)__ldg(p.eids + j0 + off + lg) : (j0 + off + lg)) : 0;
+#pragma unroll
+        for (int h = 0; h < HT; ++h) {
+          if (h < H) {
+            const float e = single ? e_reg[h]
+                                   : lrelu(__fadd_rn(__ldg(p.el + (int64_t)my_c * H + h), er_h[h]), p.slope);
+            float a = __fdiv_rn(expf(__fsub_rn(e, mx[h])), sm[h]);
+            if (p.edge_scores != nullptr && tile0 == 0) p.edge_scores[my_e * H + h] = a;
+            if (p.drop_p > 0.f) a *= drop_factor(p, my_e, h);
+            my_w[lg * HT + h] = a;
+          }
+        }
       }
+      __syncwarp();
       const int mmax = min(G, nmax - off);
       for (int t = 0; t < mmax; t += U) {
-        int cc[U], ee[U];
+        int cc[U];
         FVec<VEC> xv[U][CH];
-        float elv[U][CH];
+        float w[U][CH];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          cc[u] = __shfl_sync(FULL_MASK, my_c, t + u, G);
-          ee[u] = need_e ? __shfl_sync(FULL_MASK, my_e, t + u, G) : 0;
-        }
-        // load phase: source rows and their el values, all independent
+        for (int u = 0; u < U; ++u) cc[u] = __shfl_sync(FULL_MASK, my_c, t + u, G);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             if ((t + u) < m && colv[c]) {
               xv[u][c] = ldg_vec<VEC>(p.ft + (int64_t)cc[u] * p.D + k[c]);
-              elv[u][c] = __ldg(p.el + (int64_t)cc[u] * H + hk[c]);
+              w[u][c] = my_w[(t + u) * HT + hk[c]];
             }
           }
         }
@@ -279,32 +281,27 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatPara
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             if ((t + u) < m && colv[c]) {
-              const float e = lrelu(__fadd_rn(elv[u][c], er_c[c]), p.slope);
-              float a = __fdiv_rn(expf(__fsub_rn(e, mx_c[c])), sm_c[c]);
-              if (p.edge_scores != nullptr && k[c] == hk[c] * p.F)
-                p.edge_scores[(int64_t)ee[u] * H + hk[c]] = a;  // first lane of the head writes the score
-              if (p.drop_p > 0.f) a *= drop_factor(p, ee[u], hk[c]);
 #pragma unroll
-              for (int v = 0; v < VEC; ++v) acc[c][v] = __fadd_rn(acc[c][v], __fmul_rn(xv[u][c].v[v], a));
+              for (int v = 0; v < VEC; ++v) acc[c][v] = __fadd_rn(acc[c][v], __fmul_rn(xv[u][c].v[v], w[u][c]));
             }
           }
         }
       }
+      __syncwarp();  // the next batch overwrites the weight slots
     }
-    store_feat_tile<VEC, CH, HUB>(p, acc, colv, k, row, active, tile0, lg, gidx, n_groups, s_val);
+    store_feat_tile<VEC, CH, HUB>(p, acc, colv, k, row, active, tile0, lg, gidx, n_groups, s_buf + n_groups * HT);
   }
 }
 
 // ------------------------------------------------------------------ backward
-// SRC_PASS = false: CSC over dst rows v.  neighbour = src u: gathers ft[u], el[u]; own row: dZ[v].
+// SRC_PASS = false: CSC over dst rows v.  neighbour = src u: gathers ft[u] (owner: el[u,:]); own row: dZ[v].
 //            outputs row_pack[v,h] = {er, max, sum, S1}, grad_er[v,h].
-// SRC_PASS = true : CSR over src rows u.  neighbour = dst v: gathers dZ[v], row_pack[v]; own row: ft[u].
+// SRC_PASS = true : CSR over src rows u.  neighbour = dst v: gathers dZ[v] (owner: row_pack[v,:]); own row: ft[u].
 //            outputs grad_ft[u,:], grad_el[u,h].
 template <int VEC, int CH, int HT, bool SRC_PASS, bool HUB>
 __global__ void __launch_bounds__(kBlockThreads, 2) gat_bwd_kernel(const GatParams p) {
-  // the src pass stages a 16-byte record next to every gathered chunk: halve the batch to keep
-  // the kernel at <= 128 registers (2 CTAs / SM)
-  constexpr int U = SRC_PASS ? (CH >= 4 ? 1 : 4 / CH) : 8 / CH;
+  constexpr int U = 8 / CH;
+  __shared__ __align__(16) float s_w[(kBlockThreads + 32) * HT * 2];  // [group][edge slot][head]{a*drop, a*drop*g}
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_buf = reinterpret_cast<float*>(smem_raw);
   const int G = p.G, H = p.H;
@@ -316,70 +313,88 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_bwd_kernel(const GatPara
   const int nmax = __reduce_max_sync(FULL_MASK, n);
   const bool live = active || HUB;
   const bool need_e = p.drop_p > 0.f;
-  float* s_val = s_buf + n_groups * HT;
+  float2* my_w = reinterpret_cast<float2*>(s_w + gidx * group_stride<HT, 2>(G));
 
   const float* __restrict__ own_feat = (SRC_PASS ? p.ft : p.dZ) + row * (int64_t)p.D;
   const float* __restrict__ nb_feat = SRC_PASS ? p.dZ : p.ft;
 
-  // per-head totals (per lane until the once-per-row reduction)
+  // per-head constants of the own row (owner phase): dst pass er/max/sum, src pass el
+  float own0[HT], own1[HT], own2[HT];
+  // per-head totals: tot1/tot2 per lane until the once-per-row reduction; tot3 from the owner lanes
   float tot1[HT], tot2[HT], tot3[HT];
 #pragma unroll
-  for (int h = 0; h < HT; ++h) tot1[h] = tot2[h] = tot3[h] = 0.f;
+  for (int h = 0; h < HT; ++h) {
+    tot1[h] = tot2[h] = tot3[h] = 0.f;
+    own0[h] = own1[h] = 0.f; own2[h] = 1.f;
+    if (live && h < H) {
+      if constexpr (!SRC_PASS) {
+        own0[h] = __ldg(p.er + row * H + h);
+        own1[h] = __ldg(p.row_max + row * H + h);
+        own2[h] = __ldg(p.row_sum + row * H + h);
+      } else {
+        own0[h] = __ldg(p.el + row * H + h);
+      }
+    }
+  }
 
   for (int tile0 = 0; tile0 < p.ncols; tile0 += G * CH) {
     float acc[CH][VEC];
     FVec<VEC> ownv[CH];
-    bool colv[CH], lead[CH];
+    bool colv[CH];
     int k[CH], hk[CH];
-    float own0[CH], own1[CH], own2[CH];  // dst pass: er, max, sum of the own row;  src pass: el
-    float p1[CH], p2[CH], p3[CH];
+    float p1[CH], p2[CH];
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int vc = tile0 + c * G + lg;
       colv[c] = vc < p.ncols;
       k[c] = vc * VEC;
       hk[c] = colv[c] ? k[c] / p.F : 0;
-      lead[c] = colv[c] && (k[c] == hk[c] * p.F);  // first lane of the head: owns the per-(edge,head) terms
-      p1[c] = p2[c] = p3[c] = 0.f;
-      own0[c] = 0.f; own1[c] = 0.f; own2[c] = 1.f;
+      p1[c] = p2[c] = 0.f;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) { acc[c][v] = 0.f; ownv[c].v[v] = 0.f; }
-      if (live && colv[c]) {
-        ownv[c] = ldg_vec<VEC>(own_feat + k[c]);
-        if constexpr (!SRC_PASS) {
-          own0[c] = __ldg(p.er + row * H + hk[c]);
-          own1[c] = __ldg(p.row_max + row * H + hk[c]);
-          own2[c] = __ldg(p.row_sum + row * H + hk[c]);
-        } else {
-          own0[c] = __ldg(p.el + row * H + hk[c]);
-        }
-      }
+      if (live && colv[c]) ownv[c] = ldg_vec<VEC>(own_feat + k[c]);
     }
     for (int off = 0; off < nmax; off += G) {
       const int m = min(max(n - off, 0), G);
-      int my_c = 0, my_e = 0;
+      int my_c = 0;
       if (lg < m) {
         my_c = __ldg(p.indices + j0 + off + lg);
-        if (need_e) my_e = p.eids ? __ldg(p.eids + j0 + off + lg) : (int)(j0 + off + lg);
+        const int64_t my_e = need_e ? (p.eids ? (int64_t)__ldg(p.eids + j0 + off + lg) : (j0 + off + lg)) : 0;
+#pragma unroll
+        for (int h = 0; h < HT; ++h) {
+          if (h < H) {
+            float x, mxv, smv, s1v = 0.f;
+            if constexpr (!SRC_PASS) {
+              x = __fadd_rn(__ldg(p.el + (int64_t)my_c * H + h), own0[h]);
+              mxv = own1[h]; smv = own2[h];
+            } else {
+              const float4 pk = __ldg(p.pack + (int64_t)my_c * H + h);  // {er, max, sum, S1} of the destination
+              x = __fadd_rn(own0[h], pk.x);
+              mxv = pk.y; smv = pk.z; s1v = pk.w;
+            }
+            const float a = __fdiv_rn(expf(__fsub_rn(lrelu(x, p.slope), mxv)), smv);
+            const float g = x > 0.f ? 1.f : p.slope;
+            if (tile0 == 0) tot3[h] = fmaf(a * g, SRC_PASS ? s1v : 1.f, tot3[h]);  // S3 = sum a g | T = sum a g S1
+            const float ad = need_e ? a * drop_factor(p, my_e, h) : a;
+            my_w[lg * HT + h] = make_float2(ad, ad * g);
+          }
+        }
       }
+      __syncwarp();
       const int mmax = min(G, nmax - off);
       for (int t = 0; t < mmax; t += U) {
-        int cc[U], ee[U];
+        int cc[U];
         FVec<VEC> xv[U][CH];
-        float4 nb[U][CH];  // dst pass: .x = el[u,h];  src pass: {er, max, sum, s1} of the destination
+        float2 w[U][CH];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          cc[u] = __shfl_sync(FULL_MASK, my_c, t + u, G);
-          ee[u] = need_e ? __shfl_sync(FULL_MASK, my_e, t + u, G) : 0;
-        }
+        for (int u = 0; u < U; ++u) cc[u] = __shfl_sync(FULL_MASK, my_c, t + u, G);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             if ((t + u) < m && colv[c]) {
               xv[u][c] = ldg_vec<VEC>(nb_feat + (int64_t)cc[u] * p.D + k[c]);
-              if constexpr (!SRC_PASS) nb[u][c].x = __ldg(p.el + (int64_t)cc[u] * H + hk[c]);
-              else nb[u][c] = __ldg(p.pack + (int64_t)cc[u] * H + hk[c]);
+              w[u][c] = my_w[(t + u) * HT + hk[c]];
             }
           }
         }
@@ -388,37 +403,28 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_bwd_kernel(const GatPara
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             if ((t + u) < m && colv[c]) {
-              float x, mxv, smv;
-              if constexpr (!SRC_PASS) { x = __fadd_rn(nb[u][c].x, own0[c]); mxv = own1[c]; smv = own2[c]; }
-              else { x = __fadd_rn(own0[c], nb[u][c].x); mxv = nb[u][c].y; smv = nb[u][c].z; }
-              const float a = __fdiv_rn(expf(__fsub_rn(lrelu(x, p.slope), mxv)), smv);
-              const float g = x > 0.f ? 1.f : p.slope;
-              const float ad = need_e ? a * drop_factor(p, ee[u], hk[c]) : a;  // a * drop
               float dot = 0.f;
 #pragma unroll
               for (int v = 0; v < VEC; ++v) {
                 dot = fmaf(xv[u][c].v[v], ownv[c].v[v], dot);
-                if constexpr (SRC_PASS) acc[c][v] = __fadd_rn(acc[c][v], __fmul_rn(xv[u][c].v[v], ad));
+                if constexpr (SRC_PASS) acc[c][v] = __fadd_rn(acc[c][v], __fmul_rn(xv[u][c].v[v], w[u][c].x));
               }
-              p1[c] = fmaf(ad, dot, p1[c]);
-              p2[c] = fmaf(ad * g, dot, p2[c]);
-              if (lead[c]) {
-                if constexpr (!SRC_PASS) p3[c] = fmaf(a, g, p3[c]);                // S3 = sum a g
-                else p3[c] = fmaf(a * g, nb[u][c].w, p3[c]);                       // T  = sum a g S1[v]
-              }
+              p1[c] = fmaf(w[u][c].x, dot, p1[c]);
+              p2[c] = fmaf(w[u][c].y, dot, p2[c]);
             }
           }
         }
       }
+      __syncwarp();
     }
     // fold this tile's per-chunk partials into per-head totals (still per lane)
 #pragma unroll
     for (int c = 0; c < CH; ++c)
 #pragma unroll
       for (int h = 0; h < HT; ++h)
-        if (colv[c] && hk[c] == h) { tot1[h] += p1[c]; tot2[h] += p2[c]; tot3[h] += p3[c]; }
+        if (colv[c] && hk[c] == h) { tot1[h] += p1[c]; tot2[h] += p2[c]; }
     if constexpr (SRC_PASS) {
-      store_feat_tile<VEC, CH, HUB>(p, acc, colv, k, row, active, tile0, lg, gidx, n_groups, s_val);
+      store_feat_tile<VEC, CH, HUB>(p, acc, colv, k, row, active, tile0, lg, gidx, n_groups, s_buf + n_groups * HT);
     }
   }
   // ---- once-per-row reductions
@@ -435,8 +441,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_bwd_kernel(const GatPara
     for (int h = 0; h < HT; ++h)
       if (h == lg) {
         if constexpr (!SRC_PASS) {
-          p.out_pack[row * H + h] = make_float4(__ldg(p.er + row * H + h), __ldg(p.row_max + row * H + h),
-                                                __ldg(p.row_sum + row * H + h), tot1[h]);
+          p.out_pack[row * H + h] = make_float4(own0[h], own1[h], own2[h], tot1[h]);
           p.out_h0[row * H + h] = __fsub_rn(tot2[h], tot1[h] * tot3[h]);  // grad_er = S2 - S1*S3
         } else {
           p.out_h0[row * H + h] = __fsub_rn(tot2[h], tot3[h]);            // grad_el = sum a g dd - sum a g S1
@@ -476,24 +481,14 @@ static size_t gat_hub_smem(const GatParams& p, int vec, int ch, int ht) {
   return sizeof(float) * ((size_t)n_groups * ht + (size_t)kBlockThreads * ch * vec);
 }
 
-template <int VEC, int CH>
+template <int VEC, int CH, int HT>
 static int launch_gat_fwd(const GatParams& p, int n_hub, cudaStream_t stream) {
-  // 1. row statistics (warp per row)
-  const int64_t sblocks = (p.n_rows + (kBlockThreads / 32) - 1) / (kBlockThreads / 32);
-  gat_rowstats_kernel<false><<<(unsigned)sblocks, kBlockThreads, 0, stream>>>(p);
-  DGLB_LAUNCH_CHECK("gat_rowstats_kernel");
-  if (n_hub > 0) {
-    gat_rowstats_kernel<true><<<n_hub, kBlockThreads, 0, stream>>>(p);
-    DGLB_LAUNCH_CHECK("gat_rowstats_kernel(hub)");
-  }
-  // 2. weighted gather
   const int rows_per_block = kBlockThreads / p.G;
   const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
-  gat_fwd_kernel<VEC, CH, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+  gat_fwd_kernel<VEC, CH, HT, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
   DGLB_LAUNCH_CHECK("gat_fwd_kernel");
   if (n_hub > 0) {
-    const size_t smem = sizeof(float) * (size_t)kBlockThreads * CH * VEC;
-    gat_fwd_kernel<VEC, CH, true><<<n_hub, kBlockThreads, smem, stream>>>(p);
+    gat_fwd_kernel<VEC, CH, HT, true><<<n_hub, kBlockThreads, gat_hub_smem(p, VEC, CH, HT), stream>>>(p);
     DGLB_LAUNCH_CHECK("gat_fwd_kernel(hub)");
   }
   return DGLB_OK;
@@ -517,7 +512,14 @@ static int launch_gat_bwd(int which, const GatParams& p, int n_hub, cudaStream_t
 
 template <int VEC, int CH>
 static int dispatch_gat(int which, const GatParams& p, int ht, int n_hub, cudaStream_t stream) {
-  if (which == 0) return launch_gat_fwd<VEC, CH>(p, n_hub, stream);
+  if (which == 0) {
+    switch (ht) {
+      case 1: return launch_gat_fwd<VEC, CH, 1>(p, n_hub, stream);
+      case 2: return launch_gat_fwd<VEC, CH, 2>(p, n_hub, stream);
+      case 4: return launch_gat_fwd<VEC, CH, 4>(p, n_hub, stream);
+      default: return launch_gat_fwd<VEC, CH, 8>(p, n_hub, stream);
+    }
+  }
   switch (ht) {
     case 1: return launch_gat_bwd<VEC, CH, 1>(which, p, n_hub, stream);
     case 2: return launch_gat_bwd<VEC, CH, 2>(which, p, n_hub, stream);

@@ -281,7 +281,7 @@ def _gat_fwd(gidx, ft, el, er, slope, dropout_p, seed, want_scores=False):
                               _capi.ptr(ft), _capi.ptr(el), _capi.ptr(er), _capi.ptr(rst), _capi.ptr(row_max),
                               _capi.ptr(row_sum), _capi.ptr(scores), _capi.ptr(hub_rows), n_hub, thr, stream)
     _capi.check(rc, "dglb_gat_fused_fwd")
-    _capi.count_launch(2 + (2 if n_hub else 0))   # row statistics + weighted gather
+    _capi.count_launch(1 + (1 if n_hub else 0))
     return rst, row_max, row_sum, scores
 
 
