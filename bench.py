@@ -38,6 +38,9 @@ for _p in (ROOT, PKG):
 import numpy as np  # noqa: E402
 
 N_NODES, N_EDGES = 232965, 11606919
+# dram__bytes_read.sum + dram__bytes_write.sum of the D=602 gspmm launch, from the committed
+# `ncu --set full` capture (profiles/r01_ncu_full_summary.md): 26.74 GB + 0.58 GB
+TRAFFIC_D602 = 27317947784
 WIDTHS = (64, 128, 256, 602)
 METRIC = "gspmm copy_u_sum + gsddmm u_dot_v algorithmic HBM GB/s (reddit-shaped, D=64..602)"
 
@@ -162,12 +165,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partition-mode", default="ring", choices=["ring", "allgather"],
+                    help="N>1: ring = shard-by-shard P2P exchange overlapped with aggregation; "
+                         "allgather = one NCCL all-gather per operand, then the exact single-kernel path")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": "reddit-shaped uniform random multigraph N=232965 E=11606919 (shuffled edge order), "
                           "gspmm copy_u_sum + gsddmm u_dot_v, D in {64,128,256,602}, fp32/int32",
+              "partition": ("none" if world == 1 else "1-D rows over %d ranks, %s" % (world, args.partition_mode)),
               "l2": "no explicit flush: the sweep touches 2.0 GB of features per step, >> 126 MB L2, between reuses"}
 
     if args.impl == "reference":
@@ -198,7 +205,7 @@ def main():
     src, dst = synthetic.random_edges(N_NODES, N_NODES, N_EDGES, seed=0)
     if world > 1:
         from dgl.distributed_rows import RowPartition
-        part = RowPartition.build(src, dst, N_NODES, world, rank, dev)
+        part = RowPartition.build(src, dst, N_NODES, world, rank, dev, ring=(args.partition_mode == "ring"))
         g = part.local_graph
         n_dst_local, n_edges_local = part.n_local_rows, part.n_local_edges
     else:
@@ -224,12 +231,27 @@ def main():
         ev.setdefault(key, []).append((a, b))
         return r
 
+    ring = part is not None and part.shard_blocks is not None
+
+    def sweep_ops(D, X, V, record):
+        """gspmm copy_u_sum + gsddmm u_dot_v at width D; X, V are this rank's rows when partitioned."""
+        if part is None:
+            out = timed(("gspmm_copy_u_sum", D), record, lambda: dgl.ops.gspmm(g, "copy_lhs", "sum", X, None))
+            sc = timed(("gsddmm_u_dot_v", D), record, lambda: dgl.ops.gsddmm(g, "dot", X, V))
+        elif ring:
+            out, buf = timed(("gspmm_copy_u_sum", D), record, lambda: part.ring_copy_u_sum(X))
+            done = (buf, [(r, None) for r in range(world)])
+            sc = timed(("gsddmm_u_dot_v", D), record, lambda: part.ring_u_dot_v(X, V, gathered=done))
+        else:
+            Xfull = part.all_gather_rows(X)
+            out = timed(("gspmm_copy_u_sum", D), record, lambda: dgl.ops.gspmm(g, "copy_lhs", "sum", Xfull, None))
+            sc = timed(("gsddmm_u_dot_v", D), record, lambda: dgl.ops.gsddmm(g, "dot", Xfull, V))
+        return out, sc
+
     def one_step(record=False):
         for D in WIDTHS:
             X, V = feats[D]
-            Xfull = part.all_gather_rows(X) if part is not None else X
-            out = timed(("gspmm_copy_u_sum", D), record, lambda: dgl.ops.gspmm(g, "copy_lhs", "sum", Xfull, None))
-            sc = timed(("gsddmm_u_dot_v", D), record, lambda: dgl.ops.gsddmm(g, "dot", Xfull, V))
+            out, sc = sweep_ops(D, X, V, record)
         return out, sc
 
     def barrier():
@@ -282,9 +304,9 @@ def main():
                 s_main.wait_event(e)
                 X.record_stream(s_main)
                 V.record_stream(s_main)
-                Xfull = part.all_gather_rows(X) if part is not None else X
-                out = dgl.ops.gspmm(g, "copy_lhs", "sum", Xfull, None)
-                sc = dgl.ops.gsddmm(g, "dot", Xfull, V)
+                out, sc = sweep_ops(D, X, V, False)
+                if isinstance(sc, list):
+                    sc = torch.cat(sc, 0)
                 c = torch.cuda.Event()
                 c.record(s_main)
                 s_out.wait_event(c)
@@ -332,8 +354,10 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "kernel": "spmm_rows_kernel<VEC=2,CH=4,copy_lhs,sum> (gspmm copy_u_sum, D=602)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_launch": kb},
+                         "traffic": TRAFFIC_D602 if world == 1 else None, "peak_source": peak_src, "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_launch": kb,
+                         "note": ("single launch timed by its own CUDA-event pair" if world == 1 else
+                                  "N>1: the event pair spans the shard-by-shard exchange + aggregation of this rank's rows")},
             "e2e": {"value": e2e_val, "unit": "GB/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
             "gpu_launches": launches, "clocks": clocks.summary(),

@@ -123,8 +123,8 @@ int32_t dglb_default_hub_threshold(int64_t out_len) {
 int dglb_gspmm_csr(int op, int reduce, int dtype, int64_t n_rows, int64_t n_cols, int64_t nnz,
                    const int32_t* indptr, const int32_t* indices, const int32_t* eids, const void* ufeat,
                    const void* efeat, int ndim, const int64_t* lhs_shape_host, const int64_t* rhs_shape_host,
-                   void* out, int32_t* arg_u, int32_t* arg_e, const float* row_scale, const int32_t* hub_rows,
-                   int32_t n_hub, int32_t hub_threshold, void* stream) {
+                   void* out, int32_t* arg_u, int32_t* arg_e, const float* row_scale, int accumulate,
+                   const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold, void* stream) {
   DGLB_CHECK_ARG(valid_op(op, false), "gspmm: unknown op %d", op);
   DGLB_CHECK_ARG(reduce >= DGLB_REDUCE_SUM && reduce <= DGLB_REDUCE_MIN, "gspmm: unknown reducer %d", reduce);
   if (dtype != DGLB_F32) { set_error("gspmm: only f32 is implemented (dtype=%d)", dtype); return DGLB_E_UNSUPPORTED; }
@@ -132,6 +132,7 @@ int dglb_gspmm_csr(int op, int reduce, int dtype, int64_t n_rows, int64_t n_cols
   DGLB_CHECK_ARG(indptr && (indices || nnz == 0) && out, "gspmm: null graph/out pointer");
   DGLB_CHECK_ARG(op == DGLB_OP_COPY_RHS || ufeat || nnz == 0, "gspmm: op needs lhs (node) data");
   DGLB_CHECK_ARG(op == DGLB_OP_COPY_LHS || efeat || nnz == 0, "gspmm: op needs rhs (edge) data");
+  DGLB_CHECK_ARG(!accumulate || reduce == DGLB_REDUCE_SUM, "gspmm: accumulate is only defined for reducer sum");
   BcastShape b;
   int64_t rs;
   int rc = make_bcast(op, ndim, lhs_shape_host, rhs_shape_host, &b, &rs);
@@ -140,7 +141,7 @@ int dglb_gspmm_csr(int op, int reduce, int dtype, int64_t n_rows, int64_t n_cols
   if (op == DGLB_OP_COPY_RHS) { for (int d = 0; d < b.ndim; ++d) { b.lhs[d] = b.rhs[d]; b.out[d] = b.rhs[d]; } b.lhs_len = b.out_len = b.rhs_len; }
   return spmm_csr_f32(op, reduce, n_rows, n_cols, nnz, indptr, indices, eids, static_cast<const float*>(ufeat),
                       static_cast<const float*>(efeat), b, static_cast<float*>(out), arg_u, arg_e, row_scale,
-                      hub_rows, n_hub, hub_threshold, static_cast<cudaStream_t>(stream));
+                      accumulate, hub_rows, n_hub, hub_threshold, static_cast<cudaStream_t>(stream));
 }
 
 static int sddmm_common(int op, int dtype, int lhs_target, int rhs_target, int ndim, const int64_t* ls,

@@ -48,6 +48,7 @@ struct SpmmParams {
   int ncols;    // D / VEC
   int G, log2G;
   int hub_threshold;
+  int accumulate;  // sum only: add the result to the existing contents of `out`
 };
 
 template <int VEC, int CH, int RED>
@@ -185,10 +186,17 @@ spmm_rows_kernel(const SpmmParams p) {
         const int vc = tile0 + c * G + lg;
         if (vc < p.ncols) {
           FVec<VEC> o;
+          const int64_t off = row * (int64_t)p.D + (int64_t)vc * VEC;
 #pragma unroll
           for (int v = 0; v < VEC; ++v)
             o.v[v] = p.row_scale ? __fdiv_rn(acc.a[c][v], scale) : acc.a[c][v];
-          const int64_t off = row * (int64_t)p.D + (int64_t)vc * VEC;
+          if constexpr (RED == DGLB_REDUCE_SUM) {
+            if (p.accumulate) {
+              const FVec<VEC> prev = ldg_vec<VEC>(p.out + off);
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) o.v[v] = __fadd_rn(prev.v[v], o.v[v]);
+            }
+          }
           st_vec<VEC>(p.out + off, o);
           if constexpr (RED != DGLB_REDUCE_SUM) {
             if (p.arg_u) st_vec_i32<VEC>(p.arg_u + off, acc.au[c]);
@@ -256,7 +264,11 @@ spmm_hub_kernel(const SpmmParams p) {
           }
         }
         const int64_t off = row * (int64_t)p.D + kk;
-        p.out[off] = p.row_scale ? __fdiv_rn(a, scale) : a;
+        a = p.row_scale ? __fdiv_rn(a, scale) : a;
+        if constexpr (RED == DGLB_REDUCE_SUM) {
+          if (p.accumulate) a = __fadd_rn(p.out[off], a);
+        }
+        p.out[off] = a;
         if constexpr (RED != DGLB_REDUCE_SUM) {
           if (p.arg_u) p.arg_u[off] = au;
           if (p.arg_e) p.arg_e[off] = ae;
@@ -280,6 +292,7 @@ struct GenericSpmmParams {
   const float* row_scale;
   int64_t n_rows;
   int op, red;
+  int accumulate;
   BcastShape b;
 };
 
@@ -324,6 +337,7 @@ __global__ void __launch_bounds__(kBlockThreads) spmm_generic_kernel(const Gener
     else { if (acc > val) { acc = val; au = c; ae = e; } }
   }
   if (p.row_scale) acc = __fdiv_rn(acc, p.row_scale[row]);
+  if (p.accumulate) acc = __fadd_rn(p.out[idx], acc);
   p.out[idx] = acc;
   if (p.red != DGLB_REDUCE_SUM) {
     if (p.arg_u) p.arg_u[idx] = au;
@@ -386,7 +400,7 @@ static int and_vec(int a, int b) { return a < b ? a : b; }
 int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz,
                  const int32_t* indptr, const int32_t* indices, const int32_t* eids, const float* X,
                  const float* W, const BcastShape& b, float* out, int32_t* arg_u, int32_t* arg_e,
-                 const float* row_scale, const int32_t* hub_rows, int32_t n_hub,
+                 const float* row_scale, int accumulate, const int32_t* hub_rows, int32_t n_hub,
                  int32_t hub_threshold, cudaStream_t stream) {
   (void)n_cols;
   (void)nnz;
@@ -423,6 +437,7 @@ int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz
     p.row_scale = row_scale; p.hub_rows = hub_rows;
     p.n_rows = n_rows; p.D = (int)b.out_len; p.rhs_len = (int)b.rhs_len; p.inner = (int)inner;
     p.hub_threshold = (n_hub > 0 && hub_rows) ? hub_threshold : INT32_MAX;
+    p.accumulate = accumulate;
     if (!(n_hub > 0 && hub_rows)) n_hub = 0;
     int vec = pick_vec(b.out_len, out);
     if (use_l) vec = and_vec(vec, pick_vec(b.out_len, X));
@@ -441,7 +456,7 @@ int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz
   GenericSpmmParams g;
   g.indptr = indptr; g.indices = indices; g.eids = eids; g.X = X; g.W = W; g.out = out;
   g.arg_u = arg_u; g.arg_e = arg_e; g.row_scale = row_scale; g.n_rows = n_rows;
-  g.op = op; g.red = reduce; g.b = b;
+  g.op = op; g.red = reduce; g.b = b; g.accumulate = accumulate;
   (void)use_r;
   const int64_t total = n_rows * b.out_len;
   const int64_t blocks = (total + kBlockThreads - 1) / kBlockThreads;

@@ -41,7 +41,7 @@ _SIGNATURES = {
     "dglb_csr_find_hub_rows": (_int, [_i64, _vp, _i32, _vp, _i64, _vp, _vp]),
     "dglb_default_hub_threshold": (_i32, [_i64]),
     "dglb_gspmm_csr": (_int, [_int, _int, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _shape_t,
-                              _shape_t, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+                              _shape_t, _vp, _vp, _vp, _vp, _int, _vp, _i32, _i32, _vp]),
     "dglb_gsddmm_csr": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int,
                                _shape_t, _shape_t, _vp, _vp, _i32, _i32, _vp]),
     "dglb_gsddmm_coo": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _shape_t,

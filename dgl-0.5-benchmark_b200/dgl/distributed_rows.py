@@ -17,9 +17,13 @@ by BASELINE.json's north_star.  Scheme:
     output row is accumulated in exactly the order the single-GPU kernel uses: P-way results are
     bit-identical to 1-GPU results for sums, arg-max and structure.
 
-The all-gather is issued on a side stream; aggregation over local-source edges can run meanwhile
-(`overlap=True` splits the block into a local-source and a remote-source part; the two partial sums
-are added, which changes the summation order -- tolerance instead of bit-equality).
+Overlap (`ring=True`): the rank's CSC slice is further split by SOURCE OWNER into P column blocks.
+The feature shards travel in P-1 point-to-point rounds (round k: receive the shard of rank r+k, send
+ours to rank r-k -- every NVLink direction busy, NVSwitch gives all pairs full bandwidth); all rounds
+are queued up front on the communication stream, and the compute stream aggregates block (r+k) as
+soon as round k has landed, accumulating into the output (`dglb_gspmm_csr(..., accumulate=1)`), so
+the transfer of shard k+1 hides behind the aggregation of shard k.  The block order changes the
+summation order: results match the exact path to tolerance, not bit for bit.
 """
 import numpy as np
 import torch
@@ -57,10 +61,10 @@ class RowPartition:
         self.n_local_edges = n_local_edges
         self.group = group
         self.sizes = [hi - lo for lo, hi in ranges]
-        self._side = None
+        self.shard_blocks = None            # ring mode: block[r] = edges whose source lives on rank r
 
     @staticmethod
-    def build(src, dst, n_nodes, world, rank, device, overlap=False, group=None):
+    def build(src, dst, n_nodes, world, rank, device, overlap=False, group=None, ring=False):
         src = np.asarray(src, dtype=np.int64)
         dst = np.asarray(dst, dtype=np.int64)
         indeg = np.bincount(dst, minlength=n_nodes)
@@ -78,7 +82,15 @@ class RowPartition:
             loc = (s_f >= lo) & (s_f < hi)
             fl = create_block((torch.from_numpy(s_f[loc] - lo), torch.from_numpy(d_f[loc])), hi - lo, hi - lo).int().to(device)
             fr = create_block((torch.from_numpy(s_f[~loc]), torch.from_numpy(d_f[~loc])), n_nodes, hi - lo).int().to(device)
-        return RowPartition(n_nodes, world, rank, ranges, fwd, bwd, fl, fr, int(sel.sum()), group)
+        part = RowPartition(n_nodes, world, rank, ranges, fwd, bwd, fl, fr, int(sel.sum()), group)
+        if ring:
+            owner = np.searchsorted(np.array([r[1] for r in ranges]), s_f, side="right")
+            part.shard_blocks = []
+            for r in range(world):
+                m = owner == r
+                part.shard_blocks.append(
+                    create_block((torch.from_numpy(s_f[m]), torch.from_numpy(d_f[m])), n_nodes, hi - lo).int().to(device))
+        return part
 
     # ------------------------------------------------------------------ collectives
     def all_gather_rows(self, x_local, async_op=False):
@@ -105,6 +117,52 @@ class RowPartition:
                 out[lo:hi] = b[: hi - lo]
             work = None
         return (out, work) if async_op else out
+
+    def ring_exchange(self, x_local):
+        """Start the P-1 point-to-point rounds that fill the (N, ...) buffer with every rank's rows.
+        Returns (buffer, [(owner_rank, work or None), ...]) in arrival order, own shard first."""
+        x_local = x_local.contiguous()
+        buf = torch.empty((self.n_nodes,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+        buf[self.lo:self.hi].copy_(x_local)
+        order = [(self.rank, None)]
+        for k in range(1, self.world):
+            src_rank = (self.rank + k) % self.world
+            dst_rank = (self.rank - k) % self.world
+            lo, hi = self.ranges[src_rank]
+            ops_ = [dist.P2POp(dist.isend, x_local, dst_rank, group=self.group),
+                    dist.P2POp(dist.irecv, buf[lo:hi], src_rank, group=self.group)]
+            works = dist.batch_isend_irecv(ops_)
+            order.append((src_rank, works))
+        return buf, order
+
+    def ring_copy_u_sum(self, x_local):
+        """gspmm(copy_lhs, sum) over the rank's rows, one source shard at a time (no autograd)."""
+        from . import sparse as K
+        buf, order = self.ring_exchange(x_local)
+        out = None
+        for owner, works in order:
+            if works is not None:
+                for w in works:
+                    w.wait()
+            blk = self.shard_blocks[owner]._graph
+            if out is None:
+                out, _ = K._gspmm(blk, "copy_lhs", "sum", buf, None)
+            else:
+                K._gspmm(blk, "copy_lhs", "sum", buf, None, out=out)
+        return out, buf
+
+    def ring_u_dot_v(self, u_local, v_local, gathered=None):
+        """gsddmm(dot) for the rank's edges, per source shard; returns the per-shard (E_r, 1) results.
+        `gathered` = (buffer, order) from a ring_exchange already in flight for the same operand."""
+        from . import sparse as K
+        buf, order = gathered if gathered is not None else self.ring_exchange(u_local)
+        outs = []
+        for owner, works in order:
+            if works is not None:
+                for w in works:
+                    w.wait()
+            outs.append(K._gsddmm(self.shard_blocks[owner]._graph, "dot", buf, v_local))
+        return outs
 
     # ------------------------------------------------------------------ partitioned ops
     def copy_u_sum(self, x_local, reduce_op="sum"):

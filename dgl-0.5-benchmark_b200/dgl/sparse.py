@@ -65,11 +65,12 @@ def _check_float32(*ts):
             raise DGLError("dgl-b200 kernels compute in float32; got %s" % t.dtype)
 
 
-def _gspmm(gidx, op, reduce_op, u, e, row_scale=None):
+def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None):
     """out[v] = reduce_{(s->v)} op(u[s], e[eid]).  Returns (out, (arg_u, arg_e)).
 
     `gidx` is a GraphIndex; the kernel walks its CSC.  reduce_op in {sum, max, min}; `row_scale`
     (float32, n_dst) fuses the mean divide.  arg_u / arg_e (graph idtype) only for max / min.
+    `out` (reducer sum only): accumulate into this existing tensor instead of allocating a result.
     """
     use_u = op != "copy_rhs"
     use_e = op != "copy_lhs"
@@ -106,14 +107,17 @@ def _gspmm(gidx, op, reduce_op, u, e, row_scale=None):
     out_shape = (gidx.n_dst,) + tuple(feat_shape)
     use_cmp = reduce_op in ("max", "min")
     arg_u = arg_e = None
+    if out is not None:
+        if reduce_op != "sum" or tuple(out.shape) != out_shape or not out.is_contiguous() or out.dtype != ref.dtype:
+            raise DGLError("gspmm: `out` must be a contiguous %s tensor and the reducer must be sum" % (out_shape,))
     if gidx.n_edges == 0 or gidx.n_dst == 0:
-        v = torch.zeros(out_shape, dtype=ref.dtype, device=dev)
+        v = out if out is not None else torch.zeros(out_shape, dtype=ref.dtype, device=dev)
         if use_cmp:
             arg_u = torch.zeros(out_shape, dtype=gidx.idtype, device=dev) if use_u else None
             arg_e = torch.zeros(out_shape, dtype=gidx.idtype, device=dev) if use_e else None
     else:
         csc = gidx.csc()
-        v = torch.empty(out_shape, dtype=ref.dtype, device=dev)  # the kernel writes every row
+        v = out if out is not None else torch.empty(out_shape, dtype=ref.dtype, device=dev)  # every row is written
         if use_cmp:
             arg_u = torch.empty(out_shape, dtype=torch.int32, device=dev) if use_u else None
             arg_e = torch.empty(out_shape, dtype=torch.int32, device=dev) if use_e else None
@@ -130,7 +134,7 @@ def _gspmm(gidx, op, reduce_op, u, e, row_scale=None):
                               _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(csc.eids),
                               _capi.ptr(u), _capi.ptr(e), ndim, ls, rs,
                               _capi.ptr(v), _capi.ptr(arg_u), _capi.ptr(arg_e), _capi.ptr(row_scale),
-                              _capi.ptr(hub_rows), n_hub, thr, stream)
+                              1 if out is not None else 0, _capi.ptr(hub_rows), n_hub, thr, stream)
         _capi.check(rc, "dglb_gspmm_csr")
         _capi.count_launch(1 + (1 if n_hub else 0))
         if use_cmp and gidx.idtype != torch.int32:

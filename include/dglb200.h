@@ -126,6 +126,8 @@ int32_t dglb_default_hub_threshold(int64_t out_len);
  *    python/dgl/ops/spmm.py does).
  *  - row_scale (may be NULL): fused epilogue out[r,:] = out[r,:] / row_scale[r] (IEEE division),
  *    used for reducer "mean" with row_scale = float(clamp(in_deg,1)).
+ *  - accumulate != 0 (reducer sum only): out[r,:] += result instead of out[r,:] = result; lets a
+ *    row-partitioned caller aggregate one source shard at a time while the next shard is in flight.
  *  - hub_rows/n_hub (may be NULL/0): rows listed there (nnz > hub_threshold) are processed by
  *    the split-row path (one CTA per row) instead of the row-per-group path; the list must
  *    come from dglb_csr_find_hub_rows(indptr, hub_threshold).
@@ -136,7 +138,7 @@ int dglb_gspmm_csr(int op, int reduce, int dtype,
                    const void* ufeat, const void* efeat,
                    int ndim, const int64_t* lhs_shape_host, const int64_t* rhs_shape_host,
                    void* out, int32_t* arg_u, int32_t* arg_e,
-                   const float* row_scale,
+                   const float* row_scale, int accumulate,
                    const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
                    void* stream);
 

@@ -21,11 +21,15 @@ def _np(t):
     return None if t is None else t.detach().cpu().numpy()
 
 
-def _gspmm(gidx, op, reduce_op, u, e, row_scale=None):
+def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None):
+    prev = out
     out, (au, ae) = R._gspmm(_og(gidx), op, reduce_op, _np(u), _np(e))
     out = torch.from_numpy(np.ascontiguousarray(out))
     if row_scale is not None:
         out = out / row_scale.view((-1,) + (1,) * (out.dim() - 1))
+    if prev is not None:
+        prev += out
+        out = prev
     cv = lambda a: None if a is None else torch.from_numpy(a).to(gidx.idtype)
     return out, (cv(au), cv(ae))
 

@@ -87,6 +87,57 @@ def test_two_rank_partition_matches_single_process(oracle, overlap, kind):
         assert np.array_equal(r[6], X)                                           # ragged all-gather
 
 
+def _ring_worker(rank, world, port, q):
+    import sys
+    for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_backend
+    from dgl.distributed_rows import RowPartition
+    n, e, D = 301, 5000, 8
+    src, dst = make_edges(n, n, e, seed=5, kind="powerlaw")
+    X = np.random.default_rng(1).random((n, D), dtype=np.float32)
+    with oracle_backend.installed():
+        part = RowPartition.build(src, dst, n, world, rank, torch.device("cpu"), ring=True)
+        xl = torch.from_numpy(X[part.lo:part.hi])
+        out, buf = part.ring_copy_u_sum(xl)
+        dots = part.ring_u_dot_v(xl, xl)
+        n_blk = [b.number_of_edges() for b in part.shard_blocks]
+    q.put((rank, part.lo, part.hi, out.numpy(), buf.numpy(), [d.numpy() for d in dots], n_blk, int(part.n_local_edges)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ring_overlap_path_matches_single_process(oracle, world):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ring_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n, e, D = 301, 5000, 8
+    src, dst = make_edges(n, n, e, seed=5, kind="powerlaw")
+    X = np.random.default_rng(1).random((n, D), dtype=np.float32)
+    og = oracle.OracleGraph(src, dst, n, n)
+    want = oracle.gspmm(og, "copy_lhs", "sum", X, None)
+    got = np.concatenate([r[3] for r in res])
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)       # shard order != edge order: tolerance
+    want_dot = oracle.gsddmm(og, "dot", X, X)
+    for r in res:
+        assert np.array_equal(r[4], X)                                  # ring exchange delivered every shard
+        assert sum(r[6]) == r[7]                                        # blocks partition the rank's edges
+        got_dots = np.sort(np.concatenate(r[5]).ravel())
+        sel = (dst >= r[1]) & (dst < r[2])
+        np.testing.assert_allclose(got_dots, np.sort(want_dot[sel].ravel()), rtol=1e-6)
+
+
 def test_balanced_row_ranges():
     from dgl.distributed_rows import balanced_row_ranges
     deg = np.array([10, 0, 0, 10, 1, 1, 1, 1, 6, 10])
