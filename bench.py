@@ -165,9 +165,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--partition-mode", default="ring", choices=["ring", "allgather"],
-                    help="N>1: ring = shard-by-shard P2P exchange overlapped with aggregation; "
-                         "allgather = one NCCL all-gather per operand, then the exact single-kernel path")
+    ap.add_argument("--partition-mode", default="allgather", choices=["ring", "allgather"],
+                    help="N>1: allgather = one equal-sized NCCL all-gather per operand (the next operand's "
+                         "gather is in flight while the current one is aggregated), then the exact "
+                         "single-kernel path; ring = shard-by-shard P2P exchange + accumulate")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -249,6 +250,20 @@ def main():
         return out, sc
 
     def one_step(record=False):
+        if part is not None and not ring:
+            # software pipeline over the sweep: gather operand i+1 on the NCCL stream while operand i
+            # is aggregated on the compute stream
+            pending = part.all_gather_rows(feats[WIDTHS[0]][0], async_op=True)
+            for i, D in enumerate(WIDTHS):
+                Xfull, work = pending
+                if i + 1 < len(WIDTHS):
+                    pending = part.all_gather_rows(feats[WIDTHS[i + 1]][0], async_op=True)
+                if work is not None:
+                    work.wait()
+                V = feats[D][1]
+                out = timed(("gspmm_copy_u_sum", D), record, lambda: dgl.ops.gspmm(g, "copy_lhs", "sum", Xfull, None))
+                sc = timed(("gsddmm_u_dot_v", D), record, lambda: dgl.ops.gsddmm(g, "dot", Xfull, V))
+            return out, sc
         for D in WIDTHS:
             X, V = feats[D]
             out, sc = sweep_ops(D, X, V, record)

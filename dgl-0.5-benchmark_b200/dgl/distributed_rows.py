@@ -17,6 +17,12 @@ by BASELINE.json's north_star.  Scheme:
     output row is accumulated in exactly the order the single-GPU kernel uses: P-way results are
     bit-identical to 1-GPU results for sums, arg-max and structure.
 
+Layout of gathered operands: every rank's shard is padded to the largest shard (`max_rows`) so the
+collective is ONE equal-sized `all_gather_into_tensor` straight into the buffer the kernels read
+(ragged all-gathers fall back to per-rank broadcasts and cost 2x on 8 GPUs, profiles/r01_notes.md);
+the column indices of the rank's CSC / CSR slices are remapped once, at build time, into that padded
+id space (`owner * max_rows + local id`), so no unpacking copy is ever needed.
+
 Overlap (`ring=True`): the rank's CSC slice is further split by SOURCE OWNER into P column blocks.
 The feature shards travel in P-1 point-to-point rounds (round k: receive the shard of rank r+k, send
 ours to rank r-k -- every NVLink direction busy, NVSwitch gives all pairs full bandwidth); all rounds
@@ -62,6 +68,8 @@ class RowPartition:
         self.group = group
         self.sizes = [hi - lo for lo, hi in ranges]
         self.shard_blocks = None            # ring mode: block[r] = edges whose source lives on rank r
+        self.max_rows = max(self.sizes)
+        self.n_pad = self.max_rows * world
 
     @staticmethod
     def build(src, dst, n_nodes, world, rank, device, overlap=False, group=None, ring=False):
@@ -70,67 +78,72 @@ class RowPartition:
         indeg = np.bincount(dst, minlength=n_nodes)
         ranges = balanced_row_ranges(indeg, world)
         lo, hi = ranges[rank]
+        his = np.array([r[1] for r in ranges])
+        los = np.array([r[0] for r in ranges])
+        max_rows = int(max(h - l for l, h in ranges))
+        n_pad = max_rows * world
+
+        def pad_ids(ids):                       # global node id -> row of the padded gather buffer
+            own = np.searchsorted(his, ids, side="right")
+            return own * max_rows + (ids - los[own]), own
+
         sel = (dst >= lo) & (dst < hi)          # keeps the global (edge-id) order of the selected edges
         s_f, d_f = src[sel], dst[sel] - lo
-        fwd = create_block((torch.from_numpy(s_f), torch.from_numpy(d_f)), n_nodes, hi - lo).int().to(device)
+        s_pad, owner = pad_ids(s_f)
+        fwd = create_block((torch.from_numpy(s_pad), torch.from_numpy(d_f)), n_pad, hi - lo).int().to(device)
         selb = (src >= lo) & (src < hi)
         # backward: rows = local sources, columns = global destinations; as a block: "sources" are the
         # global dst nodes (whose dZ rows are gathered), "destinations" the local src nodes
-        bwd = create_block((torch.from_numpy(dst[selb]), torch.from_numpy(src[selb] - lo)), n_nodes, hi - lo).int().to(device)
+        bwd = create_block((torch.from_numpy(pad_ids(dst[selb])[0]), torch.from_numpy(src[selb] - lo)),
+                           n_pad, hi - lo).int().to(device)
         fl = fr = None
         if overlap:
-            loc = (s_f >= lo) & (s_f < hi)
+            loc = owner == rank
             fl = create_block((torch.from_numpy(s_f[loc] - lo), torch.from_numpy(d_f[loc])), hi - lo, hi - lo).int().to(device)
-            fr = create_block((torch.from_numpy(s_f[~loc]), torch.from_numpy(d_f[~loc])), n_nodes, hi - lo).int().to(device)
+            fr = create_block((torch.from_numpy(s_pad[~loc]), torch.from_numpy(d_f[~loc])), n_pad, hi - lo).int().to(device)
         part = RowPartition(n_nodes, world, rank, ranges, fwd, bwd, fl, fr, int(sel.sum()), group)
+        part.max_rows, part.n_pad = max_rows, n_pad
         if ring:
-            owner = np.searchsorted(np.array([r[1] for r in ranges]), s_f, side="right")
             part.shard_blocks = []
             for r in range(world):
                 m = owner == r
                 part.shard_blocks.append(
-                    create_block((torch.from_numpy(s_f[m]), torch.from_numpy(d_f[m])), n_nodes, hi - lo).int().to(device))
+                    create_block((torch.from_numpy(s_pad[m]), torch.from_numpy(d_f[m])), n_pad, hi - lo).int().to(device))
         return part
 
     # ------------------------------------------------------------------ collectives
     def all_gather_rows(self, x_local, async_op=False):
-        """Concatenate every rank's rows (ragged row counts) into the (N, ...) global tensor.
-        Equal counts: one all_gather_into_tensor.  Ragged + NCCL: grouped broadcasts straight into the
-        row slices.  Ragged + gloo (CPU tests): gather padded blocks, then copy the valid rows."""
+        """All ranks' rows in the padded layout: (world * max_rows, ...), rank r's rows starting at
+        r * max_rows (rows beyond a shard's size are padding and never referenced by the kernels).
+        One equal-sized, in-place all_gather_into_tensor."""
         x_local = x_local.contiguous()
-        out = torch.empty((self.n_nodes,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+        out = torch.empty((self.n_pad,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+        mine = out[self.rank * self.max_rows:(self.rank + 1) * self.max_rows]
+        mine[: x_local.shape[0]].copy_(x_local)
         if self.world == 1:
-            out.copy_(x_local)
             return (out, None) if async_op else out
-        if len(set(self.sizes)) == 1:
-            work = dist.all_gather_into_tensor(out, x_local, group=self.group, async_op=async_op)
-        elif dist.get_backend(self.group) == "nccl":
-            outs = [out[lo:hi] for lo, hi in self.ranges]
-            work = dist.all_gather(outs, x_local, group=self.group, async_op=async_op)
-        else:
-            mx = max(self.sizes)
-            pad = torch.zeros((mx,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
-            pad[: x_local.shape[0]] = x_local
-            buf = [torch.empty_like(pad) for _ in range(self.world)]
-            dist.all_gather(buf, pad, group=self.group)
-            for (lo, hi), b in zip(self.ranges, buf):
-                out[lo:hi] = b[: hi - lo]
-            work = None
+        work = dist.all_gather_into_tensor(out, mine, group=self.group, async_op=async_op)
         return (out, work) if async_op else out
+
+    def unpad(self, gathered):
+        """(N, ...) tensor in global node order from a padded gather buffer (tests / debugging)."""
+        return torch.cat([gathered[r * self.max_rows: r * self.max_rows + (hi - lo)]
+                          for r, (lo, hi) in enumerate(self.ranges)], 0)
 
     def ring_exchange(self, x_local):
         """Start the P-1 point-to-point rounds that fill the (N, ...) buffer with every rank's rows.
         Returns (buffer, [(owner_rank, work or None), ...]) in arrival order, own shard first."""
         x_local = x_local.contiguous()
-        buf = torch.empty((self.n_nodes,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
-        buf[self.lo:self.hi].copy_(x_local)
+        buf = torch.empty((self.n_pad,) + tuple(x_local.shape[1:]), dtype=x_local.dtype, device=x_local.device)
+        buf[self.rank * self.max_rows: self.rank * self.max_rows + x_local.shape[0]].copy_(x_local)
         order = [(self.rank, None)]
         for k in range(1, self.world):
             src_rank = (self.rank + k) % self.world
             dst_rank = (self.rank - k) % self.world
             lo, hi = self.ranges[src_rank]
             ops_ = [dist.P2POp(dist.isend, x_local, dst_rank, group=self.group),
-                    dist.P2POp(dist.irecv, buf[lo:hi], src_rank, group=self.group)]
+                    dist.P2POp(dist.irecv, buf[src_rank * self.max_rows: src_rank * self.max_rows + (hi - lo)],
+                               src_rank, group=self.group)]
             works = dist.batch_isend_irecv(ops_)
             order.append((src_rank, works))
         return buf, order

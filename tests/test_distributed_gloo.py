@@ -41,7 +41,7 @@ def _worker(rank, world, port, overlap, kind, q):
         out = part.copy_u_sum(x, "mean")
         out.backward(torch.from_numpy(dZ[part.lo:part.hi]))
         dots = part.u_dot_v(torch.from_numpy(X[part.lo:part.hi]), torch.from_numpy(X[part.lo:part.hi]))
-        gathered = part.all_gather_rows(torch.from_numpy(X[part.lo:part.hi]))
+        gathered = part.unpad(part.all_gather_rows(torch.from_numpy(X[part.lo:part.hi])))
     q.put((rank, part.lo, part.hi, out.detach().numpy(), x.grad.numpy(), dots.numpy(), gathered.numpy(),
            int(part.n_local_edges)))
     dist.barrier()
@@ -105,7 +105,8 @@ def _ring_worker(rank, world, port, q):
         out, buf = part.ring_copy_u_sum(xl)
         dots = part.ring_u_dot_v(xl, xl)
         n_blk = [b.number_of_edges() for b in part.shard_blocks]
-    q.put((rank, part.lo, part.hi, out.numpy(), buf.numpy(), [d.numpy() for d in dots], n_blk, int(part.n_local_edges)))
+    q.put((rank, part.lo, part.hi, out.numpy(), part.unpad(buf).numpy(), [d.numpy() for d in dots], n_blk,
+           int(part.n_local_edges)))
     dist.barrier()
     dist.destroy_process_group()
 
