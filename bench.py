@@ -165,17 +165,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--partition-mode", default="allgather", choices=["ring", "allgather"],
-                    help="N>1: allgather = one equal-sized NCCL all-gather per operand (the next operand's "
-                         "gather is in flight while the current one is aggregated), then the exact "
-                         "single-kernel path; ring = shard-by-shard P2P exchange + accumulate")
+    ap.add_argument("--chunks", type=int, default=4,
+                    help="N>1: each operand is all-gathered in this many equal chunks and aggregated chunk by "
+                         "chunk behind its gather (1 = one gather, then the exact single-kernel path)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": "reddit-shaped uniform random multigraph N=232965 E=11606919 (shuffled edge order), "
                           "gspmm copy_u_sum + gsddmm u_dot_v, D in {64,128,256,602}, fp32/int32",
-              "partition": ("none" if world == 1 else "1-D rows over %d ranks, %s" % (world, args.partition_mode)),
+              "partition": ("none" if world == 1 else
+                            "1-D rows over %d ranks, operands all-gathered in %d chunks" % (world, args.chunks)),
               "l2": "no explicit flush: the sweep touches 2.0 GB of features per step, >> 126 MB L2, between reuses"}
 
     if args.impl == "reference":
@@ -206,7 +206,7 @@ def main():
     src, dst = synthetic.random_edges(N_NODES, N_NODES, N_EDGES, seed=0)
     if world > 1:
         from dgl.distributed_rows import RowPartition
-        part = RowPartition.build(src, dst, N_NODES, world, rank, dev, ring=(args.partition_mode == "ring"))
+        part = RowPartition.build(src, dst, N_NODES, world, rank, dev, chunks=max(1, args.chunks))
         g = part.local_graph
         n_dst_local, n_edges_local = part.n_local_rows, part.n_local_edges
     else:
@@ -232,41 +232,25 @@ def main():
         ev.setdefault(key, []).append((a, b))
         return r
 
-    ring = part is not None and part.shard_blocks is not None
-
-    def sweep_ops(D, X, V, record):
-        """gspmm copy_u_sum + gsddmm u_dot_v at width D; X, V are this rank's rows when partitioned."""
-        if part is None:
-            out = timed(("gspmm_copy_u_sum", D), record, lambda: dgl.ops.gspmm(g, "copy_lhs", "sum", X, None))
-            sc = timed(("gsddmm_u_dot_v", D), record, lambda: dgl.ops.gsddmm(g, "dot", X, V))
-        elif ring:
-            out, buf = timed(("gspmm_copy_u_sum", D), record, lambda: part.ring_copy_u_sum(X))
-            done = (buf, [(r, None) for r in range(world)])
-            sc = timed(("gsddmm_u_dot_v", D), record, lambda: part.ring_u_dot_v(X, V, gathered=done))
-        else:
-            Xfull = part.all_gather_rows(X)
-            out = timed(("gspmm_copy_u_sum", D), record, lambda: dgl.ops.gspmm(g, "copy_lhs", "sum", Xfull, None))
-            sc = timed(("gsddmm_u_dot_v", D), record, lambda: dgl.ops.gsddmm(g, "dot", Xfull, V))
-        return out, sc
-
     def one_step(record=False):
-        if part is not None and not ring:
-            # software pipeline over the sweep: gather operand i+1 on the NCCL stream while operand i
-            # is aggregated on the compute stream
-            pending = part.all_gather_rows(feats[WIDTHS[0]][0], async_op=True)
-            for i, D in enumerate(WIDTHS):
-                Xfull, work = pending
-                if i + 1 < len(WIDTHS):
-                    pending = part.all_gather_rows(feats[WIDTHS[i + 1]][0], async_op=True)
-                if work is not None:
-                    work.wait()
-                V = feats[D][1]
-                out = timed(("gspmm_copy_u_sum", D), record, lambda: dgl.ops.gspmm(g, "copy_lhs", "sum", Xfull, None))
-                sc = timed(("gsddmm_u_dot_v", D), record, lambda: dgl.ops.gsddmm(g, "dot", Xfull, V))
+        if part is None:
+            for D in WIDTHS:
+                X, V = feats[D]
+                out = timed(("gspmm_copy_u_sum", D), record, lambda: dgl.ops.gspmm(g, "copy_lhs", "sum", X, None))
+                sc = timed(("gsddmm_u_dot_v", D), record, lambda: dgl.ops.gsddmm(g, "dot", X, V))
             return out, sc
-        for D in WIDTHS:
-            X, V = feats[D]
-            out, sc = sweep_ops(D, X, V, record)
+        # N > 1: widest operand first; the gathers of operand i+1 are queued on the NCCL stream before
+        # operand i is aggregated, and each operand is aggregated chunk by chunk behind its own gather
+        order = sorted(WIDTHS, reverse=True)
+        pending = part.all_gather_rows(feats[order[0]][0], async_op=True)
+        for i, D in enumerate(order):
+            gathered = pending
+            if i + 1 < len(order):
+                pending = part.all_gather_rows(feats[order[i + 1]][0], async_op=True)
+            V = feats[D][1]
+            out, buf = timed(("gspmm_copy_u_sum", D), record, lambda: part.pipelined_copy_u_sum(None, gathered=gathered))
+            done = (buf, [None] * part.chunks)
+            sc = timed(("gsddmm_u_dot_v", D), record, lambda: part.pipelined_u_dot_v(None, V, gathered=done))
         return out, sc
 
     def barrier():
@@ -319,9 +303,12 @@ def main():
                 s_main.wait_event(e)
                 X.record_stream(s_main)
                 V.record_stream(s_main)
-                out, sc = sweep_ops(D, X, V, False)
-                if isinstance(sc, list):
-                    sc = torch.cat(sc, 0)
+                if part is None:
+                    out = dgl.ops.gspmm(g, "copy_lhs", "sum", X, None)
+                    sc = dgl.ops.gsddmm(g, "dot", X, V)
+                else:
+                    out, buf = part.pipelined_copy_u_sum(X)
+                    sc = torch.cat(part.pipelined_u_dot_v(None, V, gathered=(buf, [None] * part.chunks)), 0)
                 c = torch.cuda.Event()
                 c.record(s_main)
                 s_out.wait_event(c)
@@ -372,7 +359,7 @@ def main():
                          "traffic": TRAFFIC_D602 if world == 1 else None, "peak_source": peak_src, "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": kb,
                          "note": ("single launch timed by its own CUDA-event pair" if world == 1 else
-                                  "N>1: the event pair spans the shard-by-shard exchange + aggregation of this rank's rows")},
+                                  "N>1: the event pair spans the chunk-by-chunk gather waits + aggregation of this rank's rows")},
             "e2e": {"value": e2e_val, "unit": "GB/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
             "gpu_launches": launches, "clocks": clocks.summary(),
