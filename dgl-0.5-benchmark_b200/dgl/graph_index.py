@@ -51,6 +51,9 @@ class CSRView:
     def hubs(self, threshold):
         """(hub_rows tensor or None, n_hub) for rows with nnz > threshold; cached per threshold."""
         hit = self._hubs.get(threshold)
+        if hit is None and self.nnz <= threshold:
+            hit = (None, 0)  # no row can hold more than nnz entries: no kernel, no sync (small batched graphs)
+            self._hubs[threshold] = hit
         if hit is None:
             dev = self.indptr.device
             n_hub_t = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -67,8 +70,10 @@ class CSRView:
         return hit
 
 
-def build_csr(n_rows, n_cols, row, col):
-    """Stable sort of (row, col) by row on the device -> CSRView."""
+def build_csr(n_rows, n_cols, row, col, row_sorted=None):
+    """Stable sort of (row, col) by row on the device -> CSRView.  `row_sorted` (True/False/None):
+    whether `row` is already non-decreasing, i.e. the edge-id permutation is the identity; when it is
+    known from the host side (graphs created from CPU tensors) the device check and its sync are skipped."""
     dev = row.device
     _capi.require_cuda(row, col)
     nnz = row.shape[0]
@@ -82,9 +87,12 @@ def build_csr(n_rows, n_cols, row, col):
     _capi.check(l.dglb_coo_to_csr(n_rows, nnz, _capi.ptr(row), _capi.ptr(col), _capi.ptr(indptr),
                                   _capi.ptr(indices), _capi.ptr(data), _capi.ptr(ws), ws_bytes, stream),
                 "dglb_coo_to_csr")
-    flag = torch.empty(1, dtype=torch.int32, device=dev)
-    _capi.check(l.dglb_is_identity_perm(nnz, _capi.ptr(data), _capi.ptr(flag), stream), "dglb_is_identity_perm")
-    identity = bool(flag.item())
+    if row_sorted is None:
+        flag = torch.empty(1, dtype=torch.int32, device=dev)
+        _capi.check(l.dglb_is_identity_perm(nnz, _capi.ptr(data), _capi.ptr(flag), stream), "dglb_is_identity_perm")
+        identity = bool(flag.item())
+    else:
+        identity = bool(row_sorted)
     return CSRView(n_rows, n_cols, indptr, indices, None if identity else data)
 
 
@@ -97,8 +105,14 @@ class GraphIndex:
         self.idtype = idtype if idtype is not None else src.dtype
         # caches shared with the reversed view
         self._c = _shared if _shared is not None else {"csc": None, "csr": None, "coo32": None,
-                                                         "formats": {"coo", "csr", "csc"}}
+                                                         "formats": {"coo", "csr", "csc"},
+                                                         "dst_sorted": None, "src_sorted": None}
         self._rev = False
+        if _shared is None and src.device.type == "cpu" and src.numel() <= (1 << 22):
+            # cheap on the host, saves a device round trip per graph (matters for batched small graphs)
+            n = src.numel()
+            self._c["dst_sorted"] = bool(n < 2 or bool((dst[1:] >= dst[:-1]).all()))
+            self._c["src_sorted"] = bool(n < 2 or bool((src[1:] >= src[:-1]).all()))
 
     # ---- basic properties
     @property
@@ -119,7 +133,7 @@ class GraphIndex:
         if idtype == self.idtype:
             return self
         g = GraphIndex(self.src.to(idtype), self.dst.to(idtype), self.n_src, self.n_dst, idtype)
-        g._c["formats"] = set(self._c["formats"])
+        self._carry(g)
         return g
 
     def to(self, device):
@@ -127,13 +141,20 @@ class GraphIndex:
         if device == self.device:
             return self
         g = GraphIndex(self.src.to(device), self.dst.to(device), self.n_src, self.n_dst, self.idtype)
-        g._c["formats"] = set(self._c["formats"])
+        self._carry(g)
         return g
 
     def restrict_formats(self, formats):
         g = GraphIndex(self.src, self.dst, self.n_src, self.n_dst, self.idtype)
+        self._carry(g)
         g._c["formats"] = set(formats)
         return g
+
+    def _carry(self, g):
+        """Copy the structure-independent cache entries to a converted copy of this (un-reversed) view."""
+        g._c["formats"] = set(self._c["formats"])
+        a, b = self._c["dst_sorted"], self._c["src_sorted"]
+        g._c["dst_sorted"], g._c["src_sorted"] = (a, b) if not self._rev else (b, a)
 
     def formats(self):
         return set(self._c["formats"])
@@ -162,9 +183,9 @@ class GraphIndex:
             n_s = self.n_src if not self._rev else self.n_dst
             n_d = self.n_dst if not self._rev else self.n_src
             if key == "csc":
-                self._c[key] = build_csr(n_d, n_s, d, s)
+                self._c[key] = build_csr(n_d, n_s, d, s, self._c["dst_sorted"])
             else:
-                self._c[key] = build_csr(n_s, n_d, s, d)
+                self._c[key] = build_csr(n_s, n_d, s, d, self._c["src_sorted"])
         return self._c[key]
 
     def csc(self):
