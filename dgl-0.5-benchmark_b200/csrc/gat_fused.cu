@@ -27,6 +27,8 @@
 //      record row_pack[v,h] = {er, max, sum, S1}.
 //   src pass (CSR): grad_ft[u] = sum a*drop*dZ[v];  grad_el[u] = sum a g (dd - S1[v]).
 // Hub rows: one CTA per row; the groups split the edges and meet in shared memory.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace dglb {
@@ -166,9 +168,9 @@ __device__ __forceinline__ void store_feat_tile(const GatParams& p, float (&acc)
 }
 
 // ------------------------------------------------------------------ forward
-template <int VEC, int CH, int HT, bool HUB>
+template <int VEC, int CH, int HT, int UT, bool HUB>
 __global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatParams p) {
-  constexpr int U = 8 / CH;
+  constexpr int U = UT / CH > 0 ? UT / CH : 1;
   __shared__ __align__(16) float s_w[(kBlockThreads + 32) * HT];  // [group][edge slot][head] weights
   extern __shared__ __align__(16) unsigned char smem_raw[];       // hub rows only
   float* s_buf = reinterpret_cast<float*>(smem_raw);
@@ -190,10 +192,26 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatPara
     er_h[h] = (h < H && live) ? __ldg(p.er + row * H + h) : 0.f;
     mx[h] = -INFINITY; sm[h] = 0.f; e_reg[h] = -INFINITY;
   }
+  // staging registers of the gather loop live at function scope: the first batch of source rows is
+  // requested BEFORE the softmax statistics (it only needs the neighbour ids), so its latency
+  // overlaps the idx -> el -> reduce chain below
+  FVec<VEC> xv[U][CH];
+  const int m_first = min(n, G);
   // ---- statistics 1: per-head max of the logits
   for (int off = 0; off < nmax; off += G) {
     const bool valid = off + lg < n;
     const int c = valid ? __ldg(p.indices + j0 + off + lg) : 0;
+    if (off == 0) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int cu = __shfl_sync(FULL_MASK, c, u, G);
+#pragma unroll
+        for (int cch = 0; cch < CH; ++cch) {
+          const int vc = cch * G + lg;
+          if (u < m_first && vc < p.ncols) xv[u][cch] = ldg_vec<VEC>(p.ft + (int64_t)cu * p.D + vc * VEC);
+        }
+      }
+    }
 #pragma unroll
     for (int h = 0; h < HT; ++h) {
       const float e = (valid && h < H) ? lrelu(__fadd_rn(__ldg(p.el + (int64_t)c * H + h), er_h[h]), p.slope)
@@ -213,7 +231,9 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatPara
       if (valid && h < H) {
         const float e = single ? e_reg[h]
                                : lrelu(__fadd_rn(__ldg(p.el + (int64_t)c * H + h), er_h[h]), p.slope);
-        sm[h] += expf(__fsub_rn(e, mx[h]));
+        const float ex = expf(__fsub_rn(e, mx[h]));
+        sm[h] += ex;
+        if (single) e_reg[h] = ex;  // single-batch rows keep exp(e - max) for the weights
       }
     }
   }
@@ -249,9 +269,10 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatPara
 #pragma unroll
         for (int h = 0; h < HT; ++h) {
           if (h < H) {
-            const float e = single ? e_reg[h]
-                                   : lrelu(__fadd_rn(__ldg(p.el + (int64_t)my_c * H + h), er_h[h]), p.slope);
-            float a = __fdiv_rn(expf(__fsub_rn(e, mx[h])), sm[h]);
+            const float ex = single ? e_reg[h]
+                                    : expf(__fsub_rn(lrelu(__fadd_rn(__ldg(p.el + (int64_t)my_c * H + h), er_h[h]),
+                                                           p.slope), mx[h]));
+            float a = __fdiv_rn(ex, sm[h]);
             if (p.edge_scores != nullptr && tile0 == 0) p.edge_scores[my_e * H + h] = a;
             if (p.drop_p > 0.f) a *= drop_factor(p, my_e, h);
             my_w[lg * HT + h] = a;
@@ -262,8 +283,8 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatPara
       const int mmax = min(G, nmax - off);
       for (int t = 0; t < mmax; t += U) {
         int cc[U];
-        FVec<VEC> xv[U][CH];
         float w[U][CH];
+        const bool prefetched = (tile0 == 0) && (off == 0) && (t == 0);  // warp-uniform
 #pragma unroll
         for (int u = 0; u < U; ++u) cc[u] = __shfl_sync(FULL_MASK, my_c, t + u, G);
 #pragma unroll
@@ -271,7 +292,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatPara
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             if ((t + u) < m && colv[c]) {
-              xv[u][c] = ldg_vec<VEC>(p.ft + (int64_t)cc[u] * p.D + k[c]);
+              if (!prefetched) xv[u][c] = ldg_vec<VEC>(p.ft + (int64_t)cc[u] * p.D + k[c]);
               w[u][c] = my_w[(t + u) * HT + hk[c]];
             }
           }
@@ -298,9 +319,9 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatPara
 //            outputs row_pack[v,h] = {er, max, sum, S1}, grad_er[v,h].
 // SRC_PASS = true : CSR over src rows u.  neighbour = dst v: gathers dZ[v] (owner: row_pack[v,:]); own row: ft[u].
 //            outputs grad_ft[u,:], grad_el[u,h].
-template <int VEC, int CH, int HT, bool SRC_PASS, bool HUB>
+template <int VEC, int CH, int HT, int UT, bool SRC_PASS, bool HUB>
 __global__ void __launch_bounds__(kBlockThreads, 2) gat_bwd_kernel(const GatParams p) {
-  constexpr int U = 8 / CH;
+  constexpr int U = UT / CH > 0 ? UT / CH : 1;
   __shared__ __align__(16) float s_w[(kBlockThreads + 32) * HT * 2];  // [group][edge slot][head]{a*drop, a*drop*g}
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_buf = reinterpret_cast<float*>(smem_raw);
@@ -481,33 +502,51 @@ static size_t gat_hub_smem(const GatParams& p, int vec, int ch, int ht) {
   return sizeof(float) * ((size_t)n_groups * ht + (size_t)kBlockThreads * ch * vec);
 }
 
-template <int VEC, int CH, int HT>
-static int launch_gat_fwd(const GatParams& p, int n_hub, cudaStream_t stream) {
+// gathers in flight per lane (U*CH); DGLB_GAT_UT=4 selects the lighter variant for tuning experiments
+static int gat_ut() {
+  static int ut = [] { const char* e = getenv("DGLB_GAT_UT"); return (e && atoi(e) == 4) ? 4 : 8; }();
+  return ut;
+}
+
+template <int VEC, int CH, int HT, int UT>
+static int launch_gat_fwd_ut(const GatParams& p, int n_hub, cudaStream_t stream) {
   const int rows_per_block = kBlockThreads / p.G;
   const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
-  gat_fwd_kernel<VEC, CH, HT, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+  gat_fwd_kernel<VEC, CH, HT, UT, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
   DGLB_LAUNCH_CHECK("gat_fwd_kernel");
   if (n_hub > 0) {
-    gat_fwd_kernel<VEC, CH, HT, true><<<n_hub, kBlockThreads, gat_hub_smem(p, VEC, CH, HT), stream>>>(p);
+    gat_fwd_kernel<VEC, CH, HT, UT, true><<<n_hub, kBlockThreads, gat_hub_smem(p, VEC, CH, HT), stream>>>(p);
     DGLB_LAUNCH_CHECK("gat_fwd_kernel(hub)");
   }
   return DGLB_OK;
 }
 
 template <int VEC, int CH, int HT>
-static int launch_gat_bwd(int which, const GatParams& p, int n_hub, cudaStream_t stream) {
+static int launch_gat_fwd(const GatParams& p, int n_hub, cudaStream_t stream) {
+  return gat_ut() == 4 ? launch_gat_fwd_ut<VEC, CH, HT, 4>(p, n_hub, stream)
+                       : launch_gat_fwd_ut<VEC, CH, HT, 8>(p, n_hub, stream);
+}
+
+template <int VEC, int CH, int HT, int UT>
+static int launch_gat_bwd_ut(int which, const GatParams& p, int n_hub, cudaStream_t stream) {
   const int rows_per_block = kBlockThreads / p.G;
   const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
   const size_t smem = gat_hub_smem(p, VEC, CH, HT);
-  if (which == 1) gat_bwd_kernel<VEC, CH, HT, false, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
-  else gat_bwd_kernel<VEC, CH, HT, true, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+  if (which == 1) gat_bwd_kernel<VEC, CH, HT, UT, false, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+  else gat_bwd_kernel<VEC, CH, HT, UT, true, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
   DGLB_LAUNCH_CHECK("gat_bwd_kernel");
   if (n_hub > 0) {
-    if (which == 1) gat_bwd_kernel<VEC, CH, HT, false, true><<<n_hub, kBlockThreads, smem, stream>>>(p);
-    else gat_bwd_kernel<VEC, CH, HT, true, true><<<n_hub, kBlockThreads, smem, stream>>>(p);
+    if (which == 1) gat_bwd_kernel<VEC, CH, HT, UT, false, true><<<n_hub, kBlockThreads, smem, stream>>>(p);
+    else gat_bwd_kernel<VEC, CH, HT, UT, true, true><<<n_hub, kBlockThreads, smem, stream>>>(p);
     DGLB_LAUNCH_CHECK("gat_bwd_kernel(hub)");
   }
   return DGLB_OK;
+}
+
+template <int VEC, int CH, int HT>
+static int launch_gat_bwd(int which, const GatParams& p, int n_hub, cudaStream_t stream) {
+  return gat_ut() == 4 ? launch_gat_bwd_ut<VEC, CH, HT, 4>(which, p, n_hub, stream)
+                       : launch_gat_bwd_ut<VEC, CH, HT, 8>(which, p, n_hub, stream);
 }
 
 template <int VEC, int CH>
