@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatPara
   for (int off = 0; off < nmax; off += G) {
     const bool valid = off + lg < n;
     const int c = valid ? __ldg(p.indices + j0 + off + lg) : 0;
-    if (off == 0) {
+    if (off == 0 && p.prefetch) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int cu = __shfl_sync(FULL_MASK, c, u, G);
@@ -281,10 +281,25 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatPara
       }
       __syncwarp();
       const int mmax = min(G, nmax - off);
-      for (int t = 0; t < mmax; t += U) {
+      int t_begin = 0;
+      if (tile0 == 0 && off == 0 && p.prefetch) {
+        // first batch of the row: its source rows were requested before the statistics
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            if (u < m && colv[c]) {
+              const float w0 = my_w[u * HT + hk[c]];
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) acc[c][v] = __fadd_rn(acc[c][v], __fmul_rn(xv[u][c].v[v], w0));
+            }
+          }
+        }
+        t_begin = U;
+      }
+      for (int t = t_begin; t < mmax; t += U) {
         int cc[U];
         float w[U][CH];
-        const bool prefetched = (tile0 == 0) && (off == 0) && (t == 0);  // warp-uniform
 #pragma unroll
         for (int u = 0; u < U; ++u) cc[u] = __shfl_sync(FULL_MASK, my_c, t + u, G);
 #pragma unroll
@@ -292,7 +307,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatPara
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             if ((t + u) < m && colv[c]) {
-              if (!prefetched) xv[u][c] = ldg_vec<VEC>(p.ft + (int64_t)cc[u] * p.D + k[c]);
+              xv[u][c] = ldg_vec<VEC>(p.ft + (int64_t)cc[u] * p.D + k[c]);
               w[u][c] = my_w[(t + u) * HT + hk[c]];
             }
           }
@@ -502,9 +517,10 @@ static size_t gat_hub_smem(const GatParams& p, int vec, int ch, int ht) {
   return sizeof(float) * ((size_t)n_groups * ht + (size_t)kBlockThreads * ch * vec);
 }
 
-// gathers in flight per lane (U*CH); DGLB_GAT_UT=4 selects the lighter variant for tuning experiments
+// gathers in flight per lane (U*CH): 4 by default (80-100 registers, 3 CTAs/SM measured faster than 8
+// at 2 CTAs/SM on every GAT shape but products); DGLB_GAT_UT=8 selects the heavier variant
 static int gat_ut() {
-  static int ut = [] { const char* e = getenv("DGLB_GAT_UT"); return (e && atoi(e) == 4) ? 4 : 8; }();
+  static int ut = [] { const char* e = getenv("DGLB_GAT_UT"); return (e && atoi(e) == 8) ? 8 : 4; }();
   return ut;
 }
 
@@ -585,6 +601,8 @@ int gat_fused_f32(int which, GatParams& p, int64_t H, int64_t F, float dropout_p
   p.drop_p = dropout_p;
   p.drop_scale = 1.f / (1.f - dropout_p);
   p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
+  static const int prefetch = [] { const char* e = getenv("DGLB_GAT_PREFETCH"); return e ? atoi(e) : 1; }();
+  p.prefetch = prefetch;
 #define DGLB_CASE(V, C) if (vec == V && ch == C) return dispatch_gat<V, C>(which, p, ht, n_hub, stream);
   DGLB_CASE(4, 1) DGLB_CASE(4, 2) DGLB_CASE(4, 4)
   DGLB_CASE(2, 1) DGLB_CASE(2, 2) DGLB_CASE(2, 4)

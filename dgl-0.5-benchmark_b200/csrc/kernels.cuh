@@ -47,6 +47,7 @@ struct GatParams {
   float slope;
   float drop_p, drop_scale;  // drop_scale = 1/(1-p)
   uint32_t seed_lo, seed_hi;
+  int prefetch;              // fwd: request the first gather batch before the softmax statistics
 };
 
 // graph_build.cu
