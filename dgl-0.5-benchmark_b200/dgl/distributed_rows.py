@@ -70,6 +70,8 @@ class RowPartition:
         self.bwd_graph = None        # all destinations (padded ids) -> local sources (CSR slice, reversed)
         self.chunk_blocks = None     # K > 1: block[k] = the rank's edges whose source lies in chunk k
         self.n_local_edges = 0
+        self._fwd_geid = self._bwd_geid = None   # global edge ids of the two blocks, in block order
+        self._geid_cache = {}
 
     # ------------------------------------------------------------------ construction
     def pad_ids(self, ids):
@@ -92,8 +94,10 @@ class RowPartition:
         s_pad, s_chunk = part.pad_ids(src[sel])
         d_loc = dst[sel] - lo
         part.n_local_edges = int(sel.sum())
+        part._fwd_geid = np.nonzero(sel)[0].astype(np.int32)
         part.local_graph = create_block((torch.from_numpy(s_pad), torch.from_numpy(d_loc)), part.n_pad, hi - lo).int().to(device)
         selb = (src >= lo) & (src < hi)
+        part._bwd_geid = np.nonzero(selb)[0].astype(np.int32)
         # backward: rows = local sources, columns = all destinations; as a block the "sources" are the
         # destination nodes (whose dZ rows are gathered) and the "destinations" the local source nodes
         part.bwd_graph = create_block((torch.from_numpy(part.pad_ids(dst[selb])[0]), torch.from_numpy(src[selb] - lo)),
@@ -139,6 +143,24 @@ class RowPartition:
                     base = (k * P + r) * cr
                     parts.append(gathered[base: base + (b - a)])
         return torch.cat(parts, 0)
+
+    def global_eids(self, which):
+        """Global edge ids of the forward ('fwd') / backward ('bwd') block in the order of that block's
+        CSC (int32 device tensor): the dropout counter of the fused GAT kernels, so that the rank that
+        applies the mask forward and the rank that replays it backward agree."""
+        if which not in self._geid_cache:
+            blk = self.local_graph if which == "fwd" else self.bwd_graph
+            geid = torch.from_numpy(self._fwd_geid if which == "fwd" else self._bwd_geid).to(blk.device)
+            csc = blk._graph.csc()
+            self._geid_cache[which] = geid if csc.eids is None else geid[csc.eids.long()].contiguous()
+        return self._geid_cache[which]
+
+    def gat_attention(self, ft_local, el_local, er_local, negative_slope=0.2, dropout_p=0.0, seed=0):
+        """Row-partitioned fused GAT attention with autograd: all-gather (ft, el) forward; backward =
+        local destination pass, all-gather (row_pack, grad_rst), local source pass."""
+        H = ft_local.shape[1]
+        return _PartitionedGAT.apply(self, ft_local, el_local.reshape(-1, H), er_local.reshape(-1, H),
+                                     float(negative_slope), float(dropout_p), int(seed))
 
     # ------------------------------------------------------------------ partitioned ops
     def copy_u_sum(self, x_local, reduce_op="sum"):
@@ -207,3 +229,32 @@ class _PartitionedCopyUSum(torch.autograd.Function):
             dz_full = part.all_gather_rows(dz_local)
             dx = ops.gspmm(part.bwd_graph, "copy_lhs", "sum", dz_full, None)
         return None, dx, None
+
+
+class _PartitionedGAT(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, part, ft, el, er, slope, dropout_p, seed):
+        with torch.no_grad():
+            ft_full = part.all_gather_rows(ft)
+            el_full = part.all_gather_rows(el)
+            rst, row_max, row_sum, _ = K_._gat_fwd(part.local_graph._graph, ft_full, el_full, er.contiguous(), slope,
+                                                   dropout_p, seed, eids=part.global_eids("fwd"))
+        ctx.part, ctx.args = part, (slope, dropout_p, seed)
+        ctx.save_for_backward(ft, el, er, ft_full, el_full, row_max, row_sum)
+        return rst
+
+    @staticmethod
+    def backward(ctx, grad_rst):
+        part = ctx.part
+        slope, dropout_p, seed = ctx.args
+        ft, el, er, ft_full, el_full, row_max, row_sum = ctx.saved_tensors
+        with torch.no_grad():
+            grad_rst = grad_rst.contiguous()
+            row_pack, grad_er = K_._gat_bwd_dst(part.local_graph._graph, ft_full, el_full, er.contiguous(), row_max,
+                                                row_sum, grad_rst, slope, dropout_p, seed, eids=part.global_eids("fwd"))
+            pack_full = part.all_gather_rows(row_pack)
+            grad_full = part.all_gather_rows(grad_rst)
+            # the backward block's CSC has the LOCAL SOURCE nodes as rows and padded destination ids as columns
+            grad_ft, grad_el = K_._gat_bwd_src(part.bwd_graph._graph.csc(), ft.contiguous(), el.contiguous(), pack_full,
+                                               grad_full, slope, dropout_p, seed, eids=part.global_eids("bwd"))
+        return None, grad_ft, grad_el, grad_er, None, None, None

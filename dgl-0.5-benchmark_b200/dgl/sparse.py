@@ -262,9 +262,11 @@ def _edge_softmax_bwd(gidx, out, grad_out):
     return grad
 
 
-def _gat_fwd(gidx, ft, el, er, slope, dropout_p, seed, want_scores=False):
+def _gat_fwd(gidx, ft, el, er, slope, dropout_p, seed, want_scores=False, eids=None):
     """Fused GAT attention forward.  ft (n_src,H,F), el (n_src,H), er (n_dst,H) ->
-    rst (n_dst,H,F), row_max, row_sum (n_dst,H) [, scores (E,H)]."""
+    rst (n_dst,H,F), row_max, row_sum (n_dst,H) [, scores (E,H)].  `eids` (int32, CSC order) overrides
+    the edge ids that key the dropout mask (row-partitioned graphs pass GLOBAL edge ids so the
+    forward block and the backward block of different ranks regenerate the same mask)."""
     _check_float32(ft, el, er)
     dev = _capi.require_cuda(ft, el, er, gidx.src)
     ft, el, er = ft.contiguous(), el.contiguous(), er.contiguous()
@@ -281,7 +283,8 @@ def _gat_fwd(gidx, ft, el, er, slope, dropout_p, seed, want_scores=False):
     hub_rows, n_hub = csc.hubs(thr)
     stream = _capi.enter(dev)
     rc = l.dglb_gat_fused_fwd(_capi.F32, csc.n_rows, csc.n_cols, csc.nnz, H, F, float(slope), float(dropout_p),
-                              int(seed), _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(csc.eids),
+                              int(seed), _capi.ptr(csc.indptr), _capi.ptr(csc.indices),
+                              _capi.ptr(eids if eids is not None else csc.eids),
                               _capi.ptr(ft), _capi.ptr(el), _capi.ptr(er), _capi.ptr(rst), _capi.ptr(row_max),
                               _capi.ptr(row_sum), _capi.ptr(scores), _capi.ptr(hub_rows), n_hub, thr, stream)
     _capi.check(rc, "dglb_gat_fused_fwd")
@@ -289,35 +292,53 @@ def _gat_fwd(gidx, ft, el, er, slope, dropout_p, seed, want_scores=False):
     return rst, row_max, row_sum, scores
 
 
-def _gat_bwd(gidx, ft, el, er, row_max, row_sum, grad_rst, slope, dropout_p, seed):
-    """Fused GAT attention backward -> (grad_ft, grad_el, grad_er)."""
+def _gat_bwd_dst(gidx, ft, el, er, row_max, row_sum, grad_rst, slope, dropout_p, seed, eids=None):
+    """Destination pass of the fused GAT backward on gidx's CSC -> (row_pack (n_dst,H,4), grad_er)."""
     dev = _capi.require_cuda(ft, el, er, grad_rst, gidx.src)
     grad_rst = grad_rst.contiguous()
     H, F = ft.shape[1], ft.shape[2]
-    csc, csr = gidx.csc(), gidx.csr()
     row_pack = torch.empty((gidx.n_dst, H, 4), dtype=torch.float32, device=dev)  # {er, max, sum, s1}
     grad_er = torch.empty((gidx.n_dst, H), dtype=ft.dtype, device=dev)
-    grad_ft = torch.empty_like(ft)
-    grad_el = torch.empty((gidx.n_src, H), dtype=ft.dtype, device=dev)
-    l = _capi.lib()
-    thr = _hub_threshold(H * F)
-    stream = _capi.enter(dev)
     if gidx.n_dst:
+        csc = gidx.csc()
+        thr = _hub_threshold(H * F)
         hub_rows, n_hub = csc.hubs(thr)
-        rc = l.dglb_gat_fused_bwd_dst(_capi.F32, csc.n_rows, csc.n_cols, csc.nnz, H, F, float(slope),
-                                      float(dropout_p), int(seed), _capi.ptr(csc.indptr), _capi.ptr(csc.indices),
-                                      _capi.ptr(csc.eids), _capi.ptr(ft), _capi.ptr(el), _capi.ptr(er),
-                                      _capi.ptr(row_max), _capi.ptr(row_sum), _capi.ptr(grad_rst), _capi.ptr(row_pack),
-                                      _capi.ptr(grad_er), _capi.ptr(hub_rows), n_hub, thr, stream)
+        stream = _capi.enter(dev)
+        rc = _capi.lib().dglb_gat_fused_bwd_dst(
+            _capi.F32, csc.n_rows, csc.n_cols, csc.nnz, H, F, float(slope), float(dropout_p), int(seed),
+            _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(eids if eids is not None else csc.eids),
+            _capi.ptr(ft), _capi.ptr(el), _capi.ptr(er), _capi.ptr(row_max), _capi.ptr(row_sum), _capi.ptr(grad_rst),
+            _capi.ptr(row_pack), _capi.ptr(grad_er), _capi.ptr(hub_rows), n_hub, thr, stream)
         _capi.check(rc, "dglb_gat_fused_bwd_dst")
         _capi.count_launch(1 + (1 if n_hub else 0))
-    if gidx.n_src:
+    return row_pack, grad_er
+
+
+def _gat_bwd_src(csr, ft, el, row_pack, grad_rst, slope, dropout_p, seed, eids=None):
+    """Source pass of the fused GAT backward on a CSRView whose rows are the source nodes and whose
+    indices are destination ids -> (grad_ft (n_src,H,F), grad_el (n_src,H)).  row_pack / grad_rst are
+    indexed by destination id."""
+    dev = _capi.require_cuda(ft, el, row_pack, grad_rst)
+    grad_rst = grad_rst.contiguous()
+    H, F = ft.shape[1], ft.shape[2]
+    grad_ft = torch.empty_like(ft)
+    grad_el = torch.empty((csr.n_rows, H), dtype=ft.dtype, device=dev)
+    if csr.n_rows:
+        thr = _hub_threshold(H * F)
         hub_rows, n_hub = csr.hubs(thr)
-        rc = l.dglb_gat_fused_bwd_src(_capi.F32, csr.n_rows, csr.n_cols, csr.nnz, H, F, float(slope),
-                                      float(dropout_p), int(seed), _capi.ptr(csr.indptr), _capi.ptr(csr.indices),
-                                      _capi.ptr(csr.eids), _capi.ptr(ft), _capi.ptr(el), _capi.ptr(row_pack),
-                                      _capi.ptr(grad_rst), _capi.ptr(grad_ft), _capi.ptr(grad_el),
-                                      _capi.ptr(hub_rows), n_hub, thr, stream)
+        stream = _capi.enter(dev)
+        rc = _capi.lib().dglb_gat_fused_bwd_src(
+            _capi.F32, csr.n_rows, csr.n_cols, csr.nnz, H, F, float(slope), float(dropout_p), int(seed),
+            _capi.ptr(csr.indptr), _capi.ptr(csr.indices), _capi.ptr(eids if eids is not None else csr.eids),
+            _capi.ptr(ft), _capi.ptr(el), _capi.ptr(row_pack), _capi.ptr(grad_rst), _capi.ptr(grad_ft),
+            _capi.ptr(grad_el), _capi.ptr(hub_rows), n_hub, thr, stream)
         _capi.check(rc, "dglb_gat_fused_bwd_src")
         _capi.count_launch(1 + (1 if n_hub else 0))
+    return grad_ft, grad_el
+
+
+def _gat_bwd(gidx, ft, el, er, row_max, row_sum, grad_rst, slope, dropout_p, seed):
+    """Fused GAT attention backward -> (grad_ft, grad_el, grad_er)."""
+    row_pack, grad_er = _gat_bwd_dst(gidx, ft, el, er, row_max, row_sum, grad_rst, slope, dropout_p, seed)
+    grad_ft, grad_el = _gat_bwd_src(gidx.csr(), ft, el, row_pack, grad_rst, slope, dropout_p, seed)
     return grad_ft, grad_el, grad_er
