@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--chunks", type=int, default=4,
+    ap.add_argument("--chunks", type=int, default=2,
                     help="N>1: each operand is all-gathered in this many equal chunks and aggregated chunk by "
                          "chunk behind its gather (1 = one gather, then the exact single-kernel path)")
     args = ap.parse_args()

@@ -22,7 +22,7 @@ import torch.nn.functional as F  # noqa: E402
 
 import dgl  # noqa: E402
 from dgl import _capi  # noqa: E402
-from examples.full_graph import GAT, GraphSAGE, synthetic_task, time_epochs  # noqa: E402
+from examples.full_graph import GAT, GraphSAGE, PartGAT, synthetic_task, time_epochs  # noqa: E402
 
 # name -> (dataset shape, model, kwargs, V100 seconds/epoch published in README.md:36-46)
 CONFIGS = {
@@ -38,6 +38,8 @@ CONFIGS = {
                                             lr=0.0029739421726400865, wd=2.4222556964495987e-05, edges=2315598), 0.0798),
     "reddit_gat": ("reddit", "gat", dict(hidden=16, heads=[1, 1, 1], dropout=0.18074706609292976,
                                          lr=0.0029739421726400865, wd=2.4222556964495987e-05), 0.5532),
+    "products_gat": ("ogbn-products", "gat", dict(hidden=16, heads=[4, 4, 4], dropout=0.18074706609292976,
+                                               lr=0.0029739421726400865, wd=2.4222556964495987e-05), None),
     "reddit_full_gat": ("reddit-full", "gat", dict(hidden=16, heads=[1, 1, 1], dropout=0.18074706609292976,
                                                    lr=0.0029739421726400865, wd=2.4222556964495987e-05), 0.5532),
 }
@@ -49,8 +51,6 @@ def run_config(name, epochs, rank, world, dev, degree, unfused=False):
         shape, dev, degree=degree, self_loops=(kind == "gat"), edges=kw.get("edges"))
     n_edges = len(src)
     if world > 1:
-        if kind != "sage":
-            raise SystemExit("row-partitioned training is implemented for the SAGE configs")
         from dgl.distributed_rows import RowPartition
         part = RowPartition.build(src, dst, n, world, rank, dev)
         graph = part
@@ -70,7 +70,10 @@ def run_config(name, epochs, rank, world, dev, degree, unfused=False):
     else:
         from dgl.nn.pytorch import GATConv
         GATConv.fused = not unfused
-        model = GAT(feats.shape[1], kw["hidden"], n_classes, kw["heads"], kw["dropout"], kw["dropout"]).to(dev)
+        if world > 1:
+            model = PartGAT(feats.shape[1], kw["hidden"], n_classes, kw["heads"], kw["dropout"], kw["dropout"]).to(dev)
+        else:
+            model = GAT(feats.shape[1], kw["hidden"], n_classes, kw["heads"], kw["dropout"], kw["dropout"]).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=kw["lr"], weight_decay=kw["wd"])
     losses = []
 
@@ -81,7 +84,7 @@ def run_config(name, epochs, rank, world, dev, degree, unfused=False):
         if kind == "sage":
             loss = F.cross_entropy(out[train_idx], labels[train_idx], reduction="sum") / n_train_total
         else:
-            loss = F.nll_loss(out[train_idx], labels[train_idx])
+            loss = F.nll_loss(out[train_idx], labels[train_idx], reduction="sum") / n_train_total
         loss.backward()
         if world > 1:
             for p in model.parameters():

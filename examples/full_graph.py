@@ -83,6 +83,50 @@ class GAT(nn.Module):
         return self.layers[-1](g, h).mean(1).log_softmax(dim=-1)
 
 
+class PartGATLayer(nn.Module):
+    """GATConv math (fc -> el/er -> fused attention) on a RowPartition: the layer input holds the rank's
+    rows only; attention dropout seeds are derived from a step counter shared by all ranks."""
+
+    def __init__(self, in_feats, out_feats, heads, feat_drop=0.0, attn_drop=0.0, negative_slope=0.2, activation=None):
+        super().__init__()
+        self.H, self.F, self.slope, self.activation = heads, out_feats, negative_slope, activation
+        self.fc = nn.Linear(in_feats, out_feats * heads, bias=False)
+        self.attn_l = nn.Parameter(torch.empty(1, heads, out_feats))
+        self.attn_r = nn.Parameter(torch.empty(1, heads, out_feats))
+        self.feat_drop, self.attn_p = nn.Dropout(feat_drop), attn_drop
+        gain = nn.init.calculate_gain("relu")
+        nn.init.xavier_normal_(self.fc.weight, gain=gain)
+        nn.init.xavier_normal_(self.attn_l, gain=gain)
+        nn.init.xavier_normal_(self.attn_r, gain=gain)
+        self.calls = 0
+
+    def forward(self, part, h):
+        ft = self.fc(self.feat_drop(h)).view(-1, self.H, self.F)
+        el = (ft * self.attn_l).sum(-1)
+        er = (ft * self.attn_r).sum(-1)
+        self.calls += 1
+        p = self.attn_p if self.training else 0.0
+        rst = part.gat_attention(ft, el, er, self.slope, p, seed=1000003 * self.calls + 17)
+        return self.activation(rst) if self.activation is not None else rst
+
+
+class PartGAT(nn.Module):
+    """The GAT of main_dgl_arxiv_gat.py:14-63 on a row partition."""
+
+    def __init__(self, in_feats, n_hidden, n_classes, heads, feat_drop=0.0, attn_drop=0.0):
+        super().__init__()
+        n = len(heads)
+        self.layers = nn.ModuleList([PartGATLayer(in_feats, n_hidden, heads[0], 0.0, 0.0, activation=F.elu)])
+        for l in range(n - 2):
+            self.layers.append(PartGATLayer(n_hidden * heads[l], n_hidden, heads[l + 1], feat_drop, attn_drop, activation=F.elu))
+        self.layers.append(PartGATLayer(n_hidden * heads[-2], n_classes, heads[-1], feat_drop, attn_drop))
+
+    def forward(self, part, h):
+        for layer in self.layers[:-1]:
+            h = layer(part, h).flatten(1)
+        return self.layers[-1](part, h).mean(1).log_softmax(dim=-1)
+
+
 def synthetic_task(name, device, seed=0, degree="uniform", self_loops=False, edges=None):
     """(graph on device, features, labels, train index) with the shape of dataset `name`."""
     n, e, d, c = synthetic.SHAPES[name]
