@@ -158,9 +158,12 @@ class RowPartition:
     def gat_attention(self, ft_local, el_local, er_local, negative_slope=0.2, dropout_p=0.0, seed=0):
         """Row-partitioned fused GAT attention with autograd: all-gather (ft, el) forward; backward =
         local destination pass, all-gather (row_pack, grad_rst), local source pass."""
+        from .ops.gat import pad_head_dim
         H = ft_local.shape[1]
-        return _PartitionedGAT.apply(self, ft_local, el_local.reshape(-1, H), er_local.reshape(-1, H),
-                                     float(negative_slope), float(dropout_p), int(seed))
+        ftp, F = pad_head_dim(ft_local)
+        rst = _PartitionedGAT.apply(self, ftp, el_local.reshape(-1, H), er_local.reshape(-1, H),
+                                    float(negative_slope), float(dropout_p), int(seed))
+        return rst if rst.shape[-1] == F else rst[..., :F]
 
     # ------------------------------------------------------------------ partitioned ops
     def copy_u_sum(self, x_local, reduce_op="sum"):
