@@ -111,6 +111,11 @@ int dglb_csr_find_hub_rows(int64_t n_rows, const int32_t* indptr, int32_t thresh
   return csr_find_hub_rows(n_rows, indptr, threshold, hub_rows, cap, n_hub, static_cast<cudaStream_t>(stream));
 }
 
+size_t dglb_hub_workspace_bytes(int64_t n_seg, int64_t out_len, int with_args) {
+  if (n_seg <= 0 || out_len <= 0) return 0;
+  return (size_t)n_seg * (size_t)out_len * 4 * (with_args ? 3 : 1);
+}
+
 int32_t dglb_default_hub_threshold(int64_t out_len) {
   // bound the bytes one row-group streams (~1.5 MB) so a hub cannot become the kernel's tail
   if (out_len < 1) out_len = 1;
@@ -124,7 +129,7 @@ int dglb_gspmm_csr(int op, int reduce, int dtype, int64_t n_rows, int64_t n_cols
                    const int32_t* indptr, const int32_t* indices, const int32_t* eids, const void* ufeat,
                    const void* efeat, int ndim, const int64_t* lhs_shape_host, const int64_t* rhs_shape_host,
                    void* out, int32_t* arg_u, int32_t* arg_e, const float* row_scale, int accumulate,
-                   const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold, void* stream) {
+                   const dglb_hub_t* hub, void* stream) {
   DGLB_CHECK_ARG(valid_op(op, false), "gspmm: unknown op %d", op);
   DGLB_CHECK_ARG(reduce >= DGLB_REDUCE_SUM && reduce <= DGLB_REDUCE_MIN, "gspmm: unknown reducer %d", reduce);
   if (dtype != DGLB_F32) { set_error("gspmm: only f32 is implemented (dtype=%d)", dtype); return DGLB_E_UNSUPPORTED; }
@@ -141,7 +146,7 @@ int dglb_gspmm_csr(int op, int reduce, int dtype, int64_t n_rows, int64_t n_cols
   if (op == DGLB_OP_COPY_RHS) { for (int d = 0; d < b.ndim; ++d) { b.lhs[d] = b.rhs[d]; b.out[d] = b.rhs[d]; } b.lhs_len = b.out_len = b.rhs_len; }
   return spmm_csr_f32(op, reduce, n_rows, n_cols, nnz, indptr, indices, eids, static_cast<const float*>(ufeat),
                       static_cast<const float*>(efeat), b, static_cast<float*>(out), arg_u, arg_e, row_scale,
-                      accumulate, hub_rows, n_hub, hub_threshold, static_cast<cudaStream_t>(stream));
+                      accumulate, hub, static_cast<cudaStream_t>(stream));
 }
 
 static int sddmm_common(int op, int dtype, int lhs_target, int rhs_target, int ndim, const int64_t* ls,
@@ -163,7 +168,7 @@ static int sddmm_common(int op, int dtype, int lhs_target, int rhs_target, int n
 int dglb_gsddmm_csr(int op, int dtype, int lhs_target, int rhs_target, int64_t n_dst, int64_t n_src, int64_t nnz,
                     const int32_t* indptr, const int32_t* indices, const int32_t* eids, const void* lhs,
                     const void* rhs, int ndim, const int64_t* lhs_shape_host, const int64_t* rhs_shape_host,
-                    void* out, const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold, void* stream) {
+                    void* out, const dglb_hub_t* hub, void* stream) {
   (void)n_src;
   BcastShape b;
   int64_t rs;
@@ -174,8 +179,7 @@ int dglb_gsddmm_csr(int op, int dtype, int lhs_target, int rhs_target, int64_t n
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (lhs_target == DGLB_TARGET_U && rhs_target == DGLB_TARGET_V) {
     rc = sddmm_csr_fast_f32(op, n_dst, indptr, indices, eids, static_cast<const float*>(lhs),
-                            static_cast<const float*>(rhs), b, rs, static_cast<float*>(out), hub_rows, n_hub,
-                            hub_threshold, st);
+                            static_cast<const float*>(rhs), b, rs, static_cast<float*>(out), hub, st);
     if (rc != DGLB_E_UNSUPPORTED) return rc;
   }
   GenericSddmmParams g;
@@ -205,8 +209,10 @@ int dglb_gsddmm_coo(int op, int dtype, int lhs_target, int rhs_target, int64_t n
 }
 
 int dglb_edge_softmax_fwd(int dtype, int64_t n_dst, int64_t nnz, int64_t n_heads, const int32_t* indptr,
-                          const int32_t* eids, const void* logits, void* out, const int32_t* hub_rows,
-                          int32_t n_hub, int32_t hub_threshold, void* stream) {
+                          const int32_t* eids, const void* logits, void* out, const dglb_hub_t* hub, void* stream) {
+  const int32_t* hub_rows = hub ? hub->rows : nullptr;
+  const int32_t n_hub = hub ? hub->n_hub : 0;
+  const int32_t hub_threshold = hub ? hub->threshold : 0;
   if (dtype != DGLB_F32) { set_error("edge_softmax: only f32 is implemented"); return DGLB_E_UNSUPPORTED; }
   DGLB_CHECK_ARG(n_dst >= 0 && nnz >= 0 && n_heads >= 0 && indptr, "edge_softmax_fwd: bad sizes / null indptr");
   DGLB_CHECK_ARG(nnz == 0 || (logits && out), "edge_softmax_fwd: null data");
@@ -217,7 +223,10 @@ int dglb_edge_softmax_fwd(int dtype, int64_t n_dst, int64_t nnz, int64_t n_heads
 
 int dglb_edge_softmax_bwd(int dtype, int64_t n_dst, int64_t nnz, int64_t n_heads, const int32_t* indptr,
                           const int32_t* eids, const void* out, const void* grad_out, void* grad_logits,
-                          const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold, void* stream) {
+                          const dglb_hub_t* hub, void* stream) {
+  const int32_t* hub_rows = hub ? hub->rows : nullptr;
+  const int32_t n_hub = hub ? hub->n_hub : 0;
+  const int32_t hub_threshold = hub ? hub->threshold : 0;
   if (dtype != DGLB_F32) { set_error("edge_softmax: only f32 is implemented"); return DGLB_E_UNSUPPORTED; }
   DGLB_CHECK_ARG(n_dst >= 0 && nnz >= 0 && n_heads >= 0 && indptr, "edge_softmax_bwd: bad sizes / null indptr");
   DGLB_CHECK_ARG(nnz == 0 || (out && grad_out && grad_logits), "edge_softmax_bwd: null data");
@@ -232,8 +241,10 @@ static void gat_zero(GatParams& p) { memset(&p, 0, sizeof(p)); }
 int dglb_gat_fused_fwd(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz, int64_t n_heads, int64_t head_dim,
                        float negative_slope, float dropout_p, uint64_t seed, const int32_t* indptr,
                        const int32_t* indices, const int32_t* eids, const void* ft, const void* el, const void* er,
-                       void* rst, float* row_max, float* row_sum, void* edge_scores, const int32_t* hub_rows,
-                       int32_t n_hub, int32_t hub_threshold, void* stream) {
+                       void* rst, float* row_max, float* row_sum, void* edge_scores, const dglb_hub_t* hub, void* stream) {
+  const int32_t* hub_rows = hub ? hub->rows : nullptr;
+  const int32_t n_hub = hub ? hub->n_hub : 0;
+  const int32_t hub_threshold = hub ? hub->threshold : 0;
   (void)n_src;
   if (dtype != DGLB_F32) { set_error("gat_fused: only f32 is implemented"); return DGLB_E_UNSUPPORTED; }
   DGLB_CHECK_ARG(n_dst >= 0 && nnz >= 0 && indptr && (indices || nnz == 0), "gat_fused_fwd: bad graph");
@@ -253,8 +264,10 @@ int dglb_gat_fused_bwd_dst(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz,
                            float negative_slope, float dropout_p, uint64_t seed, const int32_t* indptr,
                            const int32_t* indices, const int32_t* eids, const void* ft, const void* el,
                            const void* er, const float* row_max, const float* row_sum, const void* grad_rst,
-                           float* row_pack, void* grad_er, const int32_t* hub_rows, int32_t n_hub,
-                           int32_t hub_threshold, void* stream) {
+                           float* row_pack, void* grad_er, const dglb_hub_t* hub, void* stream) {
+  const int32_t* hub_rows = hub ? hub->rows : nullptr;
+  const int32_t n_hub = hub ? hub->n_hub : 0;
+  const int32_t hub_threshold = hub ? hub->threshold : 0;
   (void)n_src;
   if (dtype != DGLB_F32) { set_error("gat_fused: only f32 is implemented"); return DGLB_E_UNSUPPORTED; }
   DGLB_CHECK_ARG(n_dst >= 0 && nnz >= 0 && indptr && (indices || nnz == 0), "gat_fused_bwd_dst: bad graph");
@@ -275,7 +288,10 @@ int dglb_gat_fused_bwd_src(int dtype, int64_t n_src, int64_t n_dst, int64_t nnz,
                            float negative_slope, float dropout_p, uint64_t seed, const int32_t* indptr_csr,
                            const int32_t* indices_csr, const int32_t* eids_csr, const void* ft, const void* el,
                            const float* row_pack, const void* grad_rst, void* grad_ft, void* grad_el,
-                           const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold, void* stream) {
+                           const dglb_hub_t* hub, void* stream) {
+  const int32_t* hub_rows = hub ? hub->rows : nullptr;
+  const int32_t n_hub = hub ? hub->n_hub : 0;
+  const int32_t hub_threshold = hub ? hub->threshold : 0;
   (void)n_dst;
   if (dtype != DGLB_F32) { set_error("gat_fused: only f32 is implemented"); return DGLB_E_UNSUPPORTED; }
   DGLB_CHECK_ARG(n_src >= 0 && nnz >= 0 && indptr_csr && (indices_csr || nnz == 0), "gat_fused_bwd_src: bad graph");

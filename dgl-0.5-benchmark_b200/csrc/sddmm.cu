@@ -25,6 +25,9 @@ struct SddmmParams {
   const float* __restrict__ V;  // rhs rows, one per destination row
   float* __restrict__ out;
   const int32_t* __restrict__ hub_rows;
+  const int32_t* __restrict__ seg_ptr;  // [n_hub+1] first segment of each hub row
+  const int32_t* __restrict__ seg_hub;  // [n_seg]   hub index of each segment
+  int seg_len;
   int64_t n_rows;
   int D;      // floats per node row
   int ncols;  // D / VEC
@@ -44,7 +47,8 @@ __device__ __forceinline__ float ew_op(float l, float r) {
   else return r;
 }
 
-// (row, first CSR position, count) of the calling group; HUB: CTA per hub row, groups take slices
+// (row, first CSR position, count) of the calling group; HUB: one CTA per hub-row SEGMENT (<= seg_len
+// edges), its groups take contiguous slices -- edges are independent, so nothing is combined
 template <bool HUB>
 __device__ __forceinline__ void group_work(const SddmmParams& p, int64_t& row, int64_t& j0, int& n) {
   if constexpr (!HUB) {
@@ -58,11 +62,14 @@ __device__ __forceinline__ void group_work(const SddmmParams& p, int64_t& row, i
       row = 0;
     }
   } else {
-    row = p.hub_rows[blockIdx.x];
+    const int seg = blockIdx.x;
+    const int hub = __ldg(p.seg_hub + seg);
+    row = __ldg(p.hub_rows + hub);
+    const int k = seg - __ldg(p.seg_ptr + hub);
     const int n_groups = kBlockThreads >> p.log2G;
     const int gidx = threadIdx.x >> p.log2G;
-    const int s = __ldg(p.indptr + row);
-    const int d = __ldg(p.indptr + row + 1) - s;
+    const int s = __ldg(p.indptr + row) + k * p.seg_len;
+    const int d = min(p.seg_len, __ldg(p.indptr + row + 1) - s);
     const int per = (d + n_groups - 1) / n_groups;
     const int b = min(gidx * per, d);
     j0 = (int64_t)s + b;
@@ -400,8 +407,7 @@ static int dispatch_ew(const SddmmParams& p, int vec, int ch, int n_hub, cudaStr
 // returns DGLB_E_UNSUPPORTED (without setting an error) when the vector path does not apply
 int sddmm_csr_fast_f32(int op, int64_t n_dst, const int32_t* indptr, const int32_t* indices,
                        const int32_t* eids, const float* Uf, const float* Vf, const BcastShape& b,
-                       int64_t reduce_size, float* out, const int32_t* hub_rows, int32_t n_hub,
-                       int32_t hub_threshold, cudaStream_t stream) {
+                       int64_t reduce_size, float* out, const dglb_hub_t* hub, cudaStream_t stream) {
   if (b.lhs_len != b.rhs_len) return DGLB_E_UNSUPPORTED;
   for (int d = 0; d < b.ndim; ++d)
     if (b.lhs[d] != b.rhs[d]) return DGLB_E_UNSUPPORTED;
@@ -409,9 +415,15 @@ int sddmm_csr_fast_f32(int op, int64_t n_dst, const int32_t* indptr, const int32
   if (D <= 0 || D >= (1 << 30)) return DGLB_E_UNSUPPORTED;
   SddmmParams p;
   p.indptr = indptr; p.indices = indices; p.eids = eids; p.U = Uf; p.V = Vf; p.out = out;
-  p.hub_rows = hub_rows; p.n_rows = n_dst; p.D = (int)D;
-  p.hub_threshold = (n_hub > 0 && hub_rows) ? hub_threshold : INT32_MAX;
-  if (!(n_hub > 0 && hub_rows)) n_hub = 0;
+  const bool use_hub = hub && hub->n_hub > 0 && hub->n_seg > 0 && hub->rows && hub->seg_ptr && hub->seg_hub &&
+                       hub->seg_len > 0;
+  p.hub_rows = use_hub ? hub->rows : nullptr;
+  p.seg_ptr = use_hub ? hub->seg_ptr : nullptr;
+  p.seg_hub = use_hub ? hub->seg_hub : nullptr;
+  p.seg_len = use_hub ? hub->seg_len : 0;
+  p.n_rows = n_dst; p.D = (int)D;
+  p.hub_threshold = use_hub ? hub->threshold : INT32_MAX;
+  const int n_hub = use_hub ? hub->n_seg : 0;  // hub launches are sized by SEGMENTS
   int vec = 4;
   if (op != DGLB_OP_COPY_RHS) vec = min_int(vec, pick_vec(D, Uf));
   if (op != DGLB_OP_COPY_LHS) vec = min_int(vec, pick_vec(D, Vf));

@@ -18,9 +18,11 @@
 //     non-contracted fp32 ops, which reproduces the sequential order of DGL's CPU kernel
 //     (SpMMSumCsr) bit for bit, and makes the max/min arg tie-break (first wins) exact.
 //   * hub rows (nnz > threshold, listed by dglb_csr_find_hub_rows) are skipped by the row
-//     kernel and handled by a second kernel: one CTA per hub row, its groups take contiguous
-//     slices of the row, partials meet in shared memory and are combined in slice order
-//     (deterministic, no atomics; ties still resolve to the first CSR entry).
+//     kernel and cut into segments of <= seg_len entries: one CTA per SEGMENT (a 20 000-edge hub
+//     is spread over ~30 SMs instead of crawling through one CTA), its groups take contiguous
+//     slices, partials meet in shared memory and are combined in slice order, the segment's
+//     partial row goes to a workspace, and a small second kernel folds the segments of each hub
+//     row in segment order (deterministic, no atomics; ties still resolve to the first CSR entry).
 //   * wide rows are processed in feature tiles of G*CH*VEC floats (indices re-read from L1).
 //   * anything that does not fit the vector paths (exotic broadcasts, add/sub/div with
 //     max/min) goes to a generic thread-per-(row,feature) kernel -- still CUDA, never CPU.
@@ -41,6 +43,12 @@ struct SpmmParams {
   int32_t* __restrict__ arg_e;
   const float* __restrict__ row_scale;
   const int32_t* __restrict__ hub_rows;
+  const int32_t* __restrict__ seg_ptr;   // [n_hub+1]
+  const int32_t* __restrict__ seg_hub;   // [n_seg]
+  float* __restrict__ ws_val;            // [n_seg][D] per-segment partial rows
+  int32_t* __restrict__ ws_au;           // max/min only
+  int32_t* __restrict__ ws_ae;
+  int seg_len;
   int64_t n_rows;
   int D;        // out_len
   int rhs_len;  // floats per rhs row
@@ -208,7 +216,7 @@ spmm_rows_kernel(const SpmmParams p) {
   }
 }
 
-// ------------------------------------------------------------------ hub rows: one CTA per row
+// ------------------------------------------------------------------ hub rows: one CTA per segment
 template <int VEC, int CH, int OP, int RED, int RMODE>
 __global__ void __launch_bounds__(kBlockThreads)
 spmm_hub_kernel(const SpmmParams p) {
@@ -220,22 +228,26 @@ spmm_hub_kernel(const SpmmParams p) {
   int32_t* s_au = reinterpret_cast<int32_t*>(s_val + n_groups * tile_elems);
   int32_t* s_ae = s_au + n_groups * tile_elems;
 
-  const int64_t row = p.hub_rows[blockIdx.x];
+  const int seg = blockIdx.x;
+  const int hub = __ldg(p.seg_hub + seg);
+  const int64_t row = __ldg(p.hub_rows + hub);
+  const int k = seg - __ldg(p.seg_ptr + hub);                          // segment number inside the row
   const int lg = threadIdx.x & (G - 1);
   const int gidx = threadIdx.x >> p.log2G;
   const int row_start = __ldg(p.indptr + row);
-  const int deg = __ldg(p.indptr + row + 1) - row_start;
+  const int row_deg = __ldg(p.indptr + row + 1) - row_start;
+  const int seg_begin = k * p.seg_len;
+  const int deg = min(p.seg_len, row_deg - seg_begin);                 // entries of this segment
   const int per = (deg + n_groups - 1) / n_groups;
   const int my_begin = min(gidx * per, deg);
   const int my_n = min(per, deg - my_begin);
   const int nmax = __reduce_max_sync(FULL_MASK, my_n);
-  const float scale = p.row_scale ? __ldg(p.row_scale + row) : 1.f;
 
   for (int tile0 = 0; tile0 < p.ncols; tile0 += G * CH) {
     Acc<VEC, CH, RED> acc;
     acc.init();
-    accumulate_range<VEC, CH, OP, RED, RMODE>(p, (int64_t)row_start + my_begin, my_n, nmax, lg, tile0,
-                                              acc);
+    accumulate_range<VEC, CH, OP, RED, RMODE>(p, (int64_t)row_start + seg_begin + my_begin, my_n, nmax, lg,
+                                              tile0, acc);
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int el = (c * G + lg) * VEC;
@@ -263,19 +275,41 @@ spmm_hub_kernel(const SpmmParams p) {
             combine<RED>(a, au, ae, b, s_au[g * tile_elems + el], s_ae[g * tile_elems + el]);
           }
         }
-        const int64_t off = row * (int64_t)p.D + kk;
-        a = p.row_scale ? __fdiv_rn(a, scale) : a;
-        if constexpr (RED == DGLB_REDUCE_SUM) {
-          if (p.accumulate) a = __fadd_rn(p.out[off], a);
-        }
-        p.out[off] = a;
-        if constexpr (RED != DGLB_REDUCE_SUM) {
-          if (p.arg_u) p.arg_u[off] = au;
-          if (p.arg_e) p.arg_e[off] = ae;
-        }
+        const int64_t off = (int64_t)seg * p.D + kk;
+        p.ws_val[off] = a;
+        if constexpr (RED != DGLB_REDUCE_SUM) { p.ws_au[off] = au; p.ws_ae[off] = ae; }
       }
     }
     __syncthreads();
+  }
+}
+
+// fold the per-segment partial rows of every hub row, in segment (= CSR) order
+template <int RED>
+__global__ void __launch_bounds__(kBlockThreads) spmm_hub_combine_kernel(const SpmmParams p, int n_hub) {
+  const int64_t idx = (int64_t)blockIdx.x * kBlockThreads + threadIdx.x;
+  if (idx >= (int64_t)n_hub * p.D) return;
+  const int hub = (int)(idx / p.D);
+  const int kk = (int)(idx - (int64_t)hub * p.D);
+  const int s0 = __ldg(p.seg_ptr + hub), s1 = __ldg(p.seg_ptr + hub + 1);
+  const int64_t row = __ldg(p.hub_rows + hub);
+  float a = p.ws_val[(int64_t)s0 * p.D + kk];
+  int32_t au = 0, ae = 0;
+  if constexpr (RED != DGLB_REDUCE_SUM) { au = p.ws_au[(int64_t)s0 * p.D + kk]; ae = p.ws_ae[(int64_t)s0 * p.D + kk]; }
+  for (int sg = s0 + 1; sg < s1; ++sg) {
+    const int64_t o = (int64_t)sg * p.D + kk;
+    if constexpr (RED == DGLB_REDUCE_SUM) a = __fadd_rn(a, p.ws_val[o]);
+    else combine<RED>(a, au, ae, p.ws_val[o], p.ws_au[o], p.ws_ae[o]);
+  }
+  const int64_t off = row * (int64_t)p.D + kk;
+  if (p.row_scale) a = __fdiv_rn(a, __ldg(p.row_scale + row));
+  if constexpr (RED == DGLB_REDUCE_SUM) {
+    if (p.accumulate) a = __fadd_rn(p.out[off], a);
+  }
+  p.out[off] = a;
+  if constexpr (RED != DGLB_REDUCE_SUM) {
+    if (p.arg_u) p.arg_u[off] = au;
+    if (p.arg_e) p.arg_e[off] = ae;
   }
 }
 
@@ -347,14 +381,14 @@ __global__ void __launch_bounds__(kBlockThreads) spmm_generic_kernel(const Gener
 
 // ------------------------------------------------------------------ dispatch
 template <int VEC, int CH, int OP, int RED, int RMODE>
-static int launch_fast(const SpmmParams& p, int n_hub, cudaStream_t stream) {
+static int launch_fast(const SpmmParams& p, int n_hub, int n_seg, cudaStream_t stream) {
   const int rows_per_block = kBlockThreads / p.G;
   const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
   if (blocks > 0) {
     spmm_rows_kernel<VEC, CH, OP, RED, RMODE><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
     DGLB_LAUNCH_CHECK("spmm_rows_kernel");
   }
-  if (n_hub > 0) {
+  if (n_hub > 0 && n_seg > 0) {
     const size_t smem = (size_t)kBlockThreads * CH * VEC * 4 * (RED == DGLB_REDUCE_SUM ? 1 : 3);
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
@@ -362,14 +396,17 @@ static int launch_fast(const SpmmParams& p, int n_hub, cudaStream_t stream) {
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set = true;
     }
-    spmm_hub_kernel<VEC, CH, OP, RED, RMODE><<<n_hub, kBlockThreads, smem, stream>>>(p);
+    spmm_hub_kernel<VEC, CH, OP, RED, RMODE><<<n_seg, kBlockThreads, smem, stream>>>(p);
     DGLB_LAUNCH_CHECK("spmm_hub_kernel");
+    const int64_t cblocks = ((int64_t)n_hub * p.D + kBlockThreads - 1) / kBlockThreads;
+    spmm_hub_combine_kernel<RED><<<(unsigned)cblocks, kBlockThreads, 0, stream>>>(p, n_hub);
+    DGLB_LAUNCH_CHECK("spmm_hub_combine_kernel");
   }
   return DGLB_OK;
 }
 
 template <int OP, int RED, int RMODE>
-static int dispatch_vec_ch(SpmmParams& p, int vec, int n_hub, cudaStream_t stream) {
+static int dispatch_vec_ch(SpmmParams& p, int vec, int n_hub, int n_seg, cudaStream_t stream) {
   p.ncols = p.D / vec;
   p.G = group_lanes(p.ncols);
   p.log2G = 0;
@@ -377,7 +414,7 @@ static int dispatch_vec_ch(SpmmParams& p, int vec, int n_hub, cudaStream_t strea
   const int per_lane = (p.ncols + p.G - 1) / p.G;
   const int ch = per_lane >= 4 ? 4 : (per_lane >= 2 ? 2 : 1);
 #define DGLB_CASE(V, C) \
-  if (vec == V && ch == C) return launch_fast<V, C, OP, RED, RMODE>(p, n_hub, stream);
+  if (vec == V && ch == C) return launch_fast<V, C, OP, RED, RMODE>(p, n_hub, n_seg, stream);
   DGLB_CASE(4, 1) DGLB_CASE(4, 2) DGLB_CASE(4, 4)
   DGLB_CASE(2, 1) DGLB_CASE(2, 2) DGLB_CASE(2, 4)
   DGLB_CASE(1, 1) DGLB_CASE(1, 2) DGLB_CASE(1, 4)
@@ -387,11 +424,11 @@ static int dispatch_vec_ch(SpmmParams& p, int vec, int n_hub, cudaStream_t strea
 }
 
 template <int OP, int RMODE>
-static int dispatch_red(SpmmParams& p, int red, int vec, int n_hub, cudaStream_t stream) {
+static int dispatch_red(SpmmParams& p, int red, int vec, int n_hub, int n_seg, cudaStream_t stream) {
   switch (red) {
-    case DGLB_REDUCE_SUM: return dispatch_vec_ch<OP, DGLB_REDUCE_SUM, RMODE>(p, vec, n_hub, stream);
-    case DGLB_REDUCE_MAX: return dispatch_vec_ch<OP, DGLB_REDUCE_MAX, RMODE>(p, vec, n_hub, stream);
-    default: return dispatch_vec_ch<OP, DGLB_REDUCE_MIN, RMODE>(p, vec, n_hub, stream);
+    case DGLB_REDUCE_SUM: return dispatch_vec_ch<OP, DGLB_REDUCE_SUM, RMODE>(p, vec, n_hub, n_seg, stream);
+    case DGLB_REDUCE_MAX: return dispatch_vec_ch<OP, DGLB_REDUCE_MAX, RMODE>(p, vec, n_hub, n_seg, stream);
+    default: return dispatch_vec_ch<OP, DGLB_REDUCE_MIN, RMODE>(p, vec, n_hub, n_seg, stream);
   }
 }
 
@@ -400,8 +437,7 @@ static int and_vec(int a, int b) { return a < b ? a : b; }
 int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz,
                  const int32_t* indptr, const int32_t* indices, const int32_t* eids, const float* X,
                  const float* W, const BcastShape& b, float* out, int32_t* arg_u, int32_t* arg_e,
-                 const float* row_scale, int accumulate, const int32_t* hub_rows, int32_t n_hub,
-                 int32_t hub_threshold, cudaStream_t stream) {
+                 const float* row_scale, int accumulate, const dglb_hub_t* hub, cudaStream_t stream) {
   (void)n_cols;
   (void)nnz;
   if (n_rows == 0 || b.out_len == 0) return DGLB_OK;
@@ -434,11 +470,29 @@ int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz
     SpmmParams p;
     p.indptr = indptr; p.indices = indices; p.eids = eids;
     p.X = X; p.W = W; p.out = out; p.arg_u = arg_u; p.arg_e = arg_e;
-    p.row_scale = row_scale; p.hub_rows = hub_rows;
+    p.row_scale = row_scale;
+    const bool with_args = reduce != DGLB_REDUCE_SUM;
+    const bool use_hub = hub && hub->n_hub > 0 && hub->n_seg > 0 && hub->rows && hub->seg_ptr && hub->seg_hub &&
+                         hub->seg_len > 0;
+    int n_hub = use_hub ? hub->n_hub : 0;
+    const int n_seg = use_hub ? hub->n_seg : 0;
+    if (use_hub) {
+      const size_t need = (size_t)n_seg * (size_t)b.out_len * 4 * (with_args ? 3 : 1);
+      if (!hub->workspace || hub->workspace_bytes < need) {
+        set_error("gspmm: hub workspace too small (%zu < %zu bytes)", hub->workspace_bytes, need);
+        return DGLB_E_WORKSPACE;
+      }
+      p.hub_rows = hub->rows; p.seg_ptr = hub->seg_ptr; p.seg_hub = hub->seg_hub; p.seg_len = hub->seg_len;
+      p.ws_val = static_cast<float*>(hub->workspace);
+      p.ws_au = with_args ? reinterpret_cast<int32_t*>(p.ws_val + (size_t)n_seg * b.out_len) : nullptr;
+      p.ws_ae = with_args ? p.ws_au + (size_t)n_seg * b.out_len : nullptr;
+    } else {
+      p.hub_rows = nullptr; p.seg_ptr = nullptr; p.seg_hub = nullptr; p.seg_len = 0;
+      p.ws_val = nullptr; p.ws_au = nullptr; p.ws_ae = nullptr;
+    }
     p.n_rows = n_rows; p.D = (int)b.out_len; p.rhs_len = (int)b.rhs_len; p.inner = (int)inner;
-    p.hub_threshold = (n_hub > 0 && hub_rows) ? hub_threshold : INT32_MAX;
+    p.hub_threshold = use_hub ? hub->threshold : INT32_MAX;
     p.accumulate = accumulate;
-    if (!(n_hub > 0 && hub_rows)) n_hub = 0;
     int vec = pick_vec(b.out_len, out);
     if (use_l) vec = and_vec(vec, pick_vec(b.out_len, X));
     if (rmode == RMODE_FULL) vec = and_vec(vec, pick_vec(b.out_len, W));
@@ -447,10 +501,10 @@ int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz
       if (arg_u) vec = and_vec(vec, pick_vec(b.out_len, arg_u));
       if (arg_e) vec = and_vec(vec, pick_vec(b.out_len, arg_e));
     }
-    if (op == DGLB_OP_COPY_LHS) return dispatch_red<DGLB_OP_COPY_LHS, RMODE_NONE>(p, reduce, vec, n_hub, stream);
-    if (op == DGLB_OP_COPY_RHS) return dispatch_red<DGLB_OP_COPY_RHS, RMODE_FULL>(p, reduce, vec, n_hub, stream);
-    if (rmode == RMODE_FULL) return dispatch_vec_ch<DGLB_OP_MUL, DGLB_REDUCE_SUM, RMODE_FULL>(p, vec, n_hub, stream);
-    return dispatch_vec_ch<DGLB_OP_MUL, DGLB_REDUCE_SUM, RMODE_HEAD>(p, vec, n_hub, stream);
+    if (op == DGLB_OP_COPY_LHS) return dispatch_red<DGLB_OP_COPY_LHS, RMODE_NONE>(p, reduce, vec, n_hub, n_seg, stream);
+    if (op == DGLB_OP_COPY_RHS) return dispatch_red<DGLB_OP_COPY_RHS, RMODE_FULL>(p, reduce, vec, n_hub, n_seg, stream);
+    if (rmode == RMODE_FULL) return dispatch_vec_ch<DGLB_OP_MUL, DGLB_REDUCE_SUM, RMODE_FULL>(p, vec, n_hub, n_seg, stream);
+    return dispatch_vec_ch<DGLB_OP_MUL, DGLB_REDUCE_SUM, RMODE_HEAD>(p, vec, n_hub, n_seg, stream);
   }
   // ---- generic path
   GenericSpmmParams g;

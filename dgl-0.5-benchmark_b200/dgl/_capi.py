@@ -29,6 +29,16 @@ _vp, _i64, _i32, _int, _f32, _u64 = (ctypes.c_void_p, ctypes.c_int64, ctypes.c_i
                                      ctypes.c_float, ctypes.c_uint64)
 _shape_t = ctypes.POINTER(ctypes.c_int64)
 
+
+class HubStruct(ctypes.Structure):
+    """dglb_hub_t of include/dglb200.h."""
+    _fields_ = [("rows", ctypes.c_void_p), ("seg_ptr", ctypes.c_void_p), ("seg_hub", ctypes.c_void_p),
+                ("n_hub", ctypes.c_int32), ("n_seg", ctypes.c_int32), ("seg_len", ctypes.c_int32),
+                ("threshold", ctypes.c_int32), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t)]
+
+
+_hub_t = ctypes.POINTER(HubStruct)
+
 _SIGNATURES = {
     "dglb_abi_version": (_int, []),
     "dglb_last_error": (ctypes.c_char_p, []),
@@ -40,20 +50,21 @@ _SIGNATURES = {
     "dglb_is_identity_perm": (_int, [_i64, _vp, _vp, _vp]),
     "dglb_csr_find_hub_rows": (_int, [_i64, _vp, _i32, _vp, _i64, _vp, _vp]),
     "dglb_default_hub_threshold": (_i32, [_i64]),
+    "dglb_hub_workspace_bytes": (ctypes.c_size_t, [_i64, _i64, _int]),
     "dglb_gspmm_csr": (_int, [_int, _int, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _shape_t,
-                              _shape_t, _vp, _vp, _vp, _vp, _int, _vp, _i32, _i32, _vp]),
+                              _shape_t, _vp, _vp, _vp, _vp, _int, _hub_t, _vp]),
     "dglb_gsddmm_csr": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int,
-                               _shape_t, _shape_t, _vp, _vp, _i32, _i32, _vp]),
+                               _shape_t, _shape_t, _vp, _hub_t, _vp]),
     "dglb_gsddmm_coo": (_int, [_int, _int, _int, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _shape_t,
                                _shape_t, _vp, _vp]),
-    "dglb_edge_softmax_fwd": (_int, [_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
-    "dglb_edge_softmax_bwd": (_int, [_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "dglb_edge_softmax_fwd": (_int, [_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _hub_t, _vp]),
+    "dglb_edge_softmax_bwd": (_int, [_int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _hub_t, _vp]),
     "dglb_gat_fused_fwd": (_int, [_int, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _u64, _vp, _vp, _vp, _vp,
-                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _hub_t, _vp]),
     "dglb_gat_fused_bwd_dst": (_int, [_int, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _u64, _vp, _vp, _vp,
-                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _hub_t, _vp]),
     "dglb_gat_fused_bwd_src": (_int, [_int, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _u64, _vp, _vp, _vp,
-                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _hub_t, _vp]),
 }
 
 

@@ -49,12 +49,12 @@ class CSRView:
         return self._deg_f
 
     def hubs(self, threshold):
-        """(hub_rows tensor or None, n_hub) for rows with nnz > threshold; cached per threshold."""
-        hit = self._hubs.get(threshold)
-        if hit is None and self.nnz <= threshold:
-            hit = (None, 0)  # no row can hold more than nnz entries: no kernel, no sync (small batched graphs)
-            self._hubs[threshold] = hit
-        if hit is None:
+        """HubInfo for rows with nnz > threshold (None when there are none); cached per threshold.
+        Hub rows are cut into segments of <= threshold entries (one CTA each in gspmm / gsddmm)."""
+        if threshold in self._hubs:
+            return self._hubs[threshold]
+        info = None
+        if self.nnz > threshold:  # otherwise no row can exceed it: no kernel, no sync (small batched graphs)
             dev = self.indptr.device
             n_hub_t = torch.zeros(1, dtype=torch.int32, device=dev)
             cap = max(1, min(self.n_rows, self.nnz // max(threshold, 1) + 1))
@@ -65,9 +65,36 @@ class CSRView:
                         "dglb_csr_find_hub_rows")
             n_hub = int(n_hub_t.item())  # one-off sync per (graph, threshold)
             assert n_hub <= cap
-            hit = (rows[:n_hub].contiguous() if n_hub else None, n_hub)
-            self._hubs[threshold] = hit
-        return hit
+            if n_hub:
+                rows = torch.sort(rows[:n_hub]).values.contiguous()       # deterministic order
+                deg = self.degrees()[rows.long()].cpu().numpy().astype("int64")
+                seg_len = int(threshold)
+                nseg = -(-deg // seg_len)
+                seg_ptr = torch.zeros(n_hub + 1, dtype=torch.int32)
+                seg_ptr[1:] = torch.from_numpy(nseg.cumsum()).to(torch.int32)
+                seg_hub = torch.repeat_interleave(torch.arange(n_hub, dtype=torch.int32), torch.from_numpy(nseg))
+                info = HubInfo(rows, seg_ptr.to(dev), seg_hub.to(dev), n_hub, int(nseg.sum()), seg_len, int(threshold))
+        self._hubs[threshold] = info
+        return info
+
+
+class HubInfo:
+    """Caller-owned hub-row metadata of the C-ABI (dglb_hub_t): device arrays + counts."""
+
+    __slots__ = ("rows", "seg_ptr", "seg_hub", "n_hub", "n_seg", "seg_len", "threshold")
+
+    def __init__(self, rows, seg_ptr, seg_hub, n_hub, n_seg, seg_len, threshold):
+        self.rows, self.seg_ptr, self.seg_hub = rows, seg_ptr, seg_hub
+        self.n_hub, self.n_seg, self.seg_len, self.threshold = n_hub, n_seg, seg_len, threshold
+
+    def struct(self, workspace=None):
+        """ctypes dglb_hub_t (keep the returned object alive across the call)."""
+        st = _capi.HubStruct()
+        st.rows, st.seg_ptr, st.seg_hub = self.rows.data_ptr(), self.seg_ptr.data_ptr(), self.seg_hub.data_ptr()
+        st.n_hub, st.n_seg, st.seg_len, st.threshold = self.n_hub, self.n_seg, self.seg_len, self.threshold
+        st.workspace = workspace.data_ptr() if workspace is not None else None
+        st.workspace_bytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
+        return st
 
 
 def build_csr(n_rows, n_cols, row, col, row_sorted=None):

@@ -6,6 +6,8 @@ same argument meaning (`op`, `reduce_op`, operands may be None, 1-D operands are
 same "skip the kernel when the graph has no edges" rule.  Outputs are allocated by torch;
 everything else happens in lib/libdglb200.so on the current CUDA stream.
 """
+import ctypes
+
 import torch
 
 from . import _capi
@@ -22,6 +24,18 @@ def _hub_threshold(width):
     if HUB_THRESHOLD is not None:
         return int(HUB_THRESHOLD)
     return _capi.lib().dglb_default_hub_threshold(int(width))
+
+
+def _hub_arg(info, dev=None, out_len=0, with_args=False):
+    """(ctypes pointer or None, objects to keep alive, extra launches) for a HubInfo."""
+    if info is None:
+        return None, None, 0
+    ws = None
+    if out_len:
+        nbytes = _capi.lib().dglb_hub_workspace_bytes(info.n_seg, int(out_len), 1 if with_args else 0)
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+    st = info.struct(ws)
+    return ctypes.byref(st), (st, ws), (2 if out_len else 1)
 
 
 def infer_broadcast_shape(op, shp1, shp2):
@@ -126,7 +140,7 @@ def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None):
             out_len *= s
         l = _capi.lib()
         thr = _hub_threshold(out_len)
-        hub_rows, n_hub = csc.hubs(thr)
+        hub, _keep, hub_launches = _hub_arg(csc.hubs(thr), dev, out_len, use_cmp)
         ndim, ls, rs = _shapes_for_abi(op, u, e)
         stream = _capi.enter(dev)
         rc = l.dglb_gspmm_csr(_capi.OPS[op], _capi.REDUCERS[reduce_op], _capi.F32,
@@ -134,9 +148,9 @@ def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None):
                               _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(csc.eids),
                               _capi.ptr(u), _capi.ptr(e), ndim, ls, rs,
                               _capi.ptr(v), _capi.ptr(arg_u), _capi.ptr(arg_e), _capi.ptr(row_scale),
-                              1 if out is not None else 0, _capi.ptr(hub_rows), n_hub, thr, stream)
+                              1 if out is not None else 0, hub, stream)
         _capi.check(rc, "dglb_gspmm_csr")
-        _capi.count_launch(1 + (1 if n_hub else 0))
+        _capi.count_launch(1 + hub_launches)
         if use_cmp and gidx.idtype != torch.int32:
             arg_u = arg_u.to(gidx.idtype) if arg_u is not None else None
             arg_e = arg_e.to(gidx.idtype) if arg_e is not None else None
@@ -198,13 +212,13 @@ def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
             for s in ref.shape[1:]:
                 width *= s
             thr = _hub_threshold(width)
-            hub_rows, n_hub = csc.hubs(thr)
+            hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
             rc = l.dglb_gsddmm_csr(_capi.OPS[op], _capi.F32, lt, rt, csc.n_rows, csc.n_cols, csc.nnz,
                                    _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(csc.eids),
                                    _capi.ptr(lhs), _capi.ptr(rhs), ndim, ls, rs, _capi.ptr(out),
-                                   _capi.ptr(hub_rows), n_hub, thr, stream)
+                                   hub, stream)
             _capi.check(rc, "dglb_gsddmm_csr")
-            _capi.count_launch(1 + (1 if n_hub else 0))
+            _capi.count_launch(1 + hub_launches)
         else:
             s32, d32 = gidx.coo32()
             rc = l.dglb_gsddmm_coo(_capi.OPS[op], _capi.F32, lt, rt, gidx.n_src, gidx.n_dst, gidx.n_edges,
@@ -231,12 +245,12 @@ def _edge_softmax_fwd(gidx, logits):
     csc = gidx.csc()
     l = _capi.lib()
     thr = _hub_threshold(max(heads, 64))
-    hub_rows, n_hub = csc.hubs(thr)
+    hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
     stream = _capi.enter(dev)
     rc = l.dglb_edge_softmax_fwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(csc.eids),
-                                 _capi.ptr(logits), _capi.ptr(out), _capi.ptr(hub_rows), n_hub, thr, stream)
+                                 _capi.ptr(logits), _capi.ptr(out), hub, stream)
     _capi.check(rc, "dglb_edge_softmax_fwd")
-    _capi.count_launch(1 + (1 if n_hub else 0))
+    _capi.count_launch(1 + hub_launches)
     return out
 
 
@@ -252,13 +266,12 @@ def _edge_softmax_bwd(gidx, out, grad_out):
     csc = gidx.csc()
     l = _capi.lib()
     thr = _hub_threshold(max(heads, 64))
-    hub_rows, n_hub = csc.hubs(thr)
+    hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
     stream = _capi.enter(dev)
     rc = l.dglb_edge_softmax_bwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(csc.eids),
-                                 _capi.ptr(out), _capi.ptr(grad_out), _capi.ptr(grad), _capi.ptr(hub_rows), n_hub,
-                                 thr, stream)
+                                 _capi.ptr(out), _capi.ptr(grad_out), _capi.ptr(grad), hub, stream)
     _capi.check(rc, "dglb_edge_softmax_bwd")
-    _capi.count_launch(1 + (1 if n_hub else 0))
+    _capi.count_launch(1 + hub_launches)
     return grad
 
 
@@ -280,15 +293,15 @@ def _gat_fwd(gidx, ft, el, er, slope, dropout_p, seed, want_scores=False, eids=N
     csc = gidx.csc()
     l = _capi.lib()
     thr = _hub_threshold(H * F)
-    hub_rows, n_hub = csc.hubs(thr)
+    hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
     stream = _capi.enter(dev)
     rc = l.dglb_gat_fused_fwd(_capi.F32, csc.n_rows, csc.n_cols, csc.nnz, H, F, float(slope), float(dropout_p),
                               int(seed), _capi.ptr(csc.indptr), _capi.ptr(csc.indices),
                               _capi.ptr(eids if eids is not None else csc.eids),
                               _capi.ptr(ft), _capi.ptr(el), _capi.ptr(er), _capi.ptr(rst), _capi.ptr(row_max),
-                              _capi.ptr(row_sum), _capi.ptr(scores), _capi.ptr(hub_rows), n_hub, thr, stream)
+                              _capi.ptr(row_sum), _capi.ptr(scores), hub, stream)
     _capi.check(rc, "dglb_gat_fused_fwd")
-    _capi.count_launch(1 + (1 if n_hub else 0))
+    _capi.count_launch(1 + hub_launches)
     return rst, row_max, row_sum, scores
 
 
@@ -302,15 +315,15 @@ def _gat_bwd_dst(gidx, ft, el, er, row_max, row_sum, grad_rst, slope, dropout_p,
     if gidx.n_dst:
         csc = gidx.csc()
         thr = _hub_threshold(H * F)
-        hub_rows, n_hub = csc.hubs(thr)
+        hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
         stream = _capi.enter(dev)
         rc = _capi.lib().dglb_gat_fused_bwd_dst(
             _capi.F32, csc.n_rows, csc.n_cols, csc.nnz, H, F, float(slope), float(dropout_p), int(seed),
             _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(eids if eids is not None else csc.eids),
             _capi.ptr(ft), _capi.ptr(el), _capi.ptr(er), _capi.ptr(row_max), _capi.ptr(row_sum), _capi.ptr(grad_rst),
-            _capi.ptr(row_pack), _capi.ptr(grad_er), _capi.ptr(hub_rows), n_hub, thr, stream)
+            _capi.ptr(row_pack), _capi.ptr(grad_er), hub, stream)
         _capi.check(rc, "dglb_gat_fused_bwd_dst")
-        _capi.count_launch(1 + (1 if n_hub else 0))
+        _capi.count_launch(1 + hub_launches)
     return row_pack, grad_er
 
 
@@ -325,15 +338,15 @@ def _gat_bwd_src(csr, ft, el, row_pack, grad_rst, slope, dropout_p, seed, eids=N
     grad_el = torch.empty((csr.n_rows, H), dtype=ft.dtype, device=dev)
     if csr.n_rows:
         thr = _hub_threshold(H * F)
-        hub_rows, n_hub = csr.hubs(thr)
+        hub, _keep, hub_launches = _hub_arg(csr.hubs(thr))
         stream = _capi.enter(dev)
         rc = _capi.lib().dglb_gat_fused_bwd_src(
             _capi.F32, csr.n_rows, csr.n_cols, csr.nnz, H, F, float(slope), float(dropout_p), int(seed),
             _capi.ptr(csr.indptr), _capi.ptr(csr.indices), _capi.ptr(eids if eids is not None else csr.eids),
             _capi.ptr(ft), _capi.ptr(el), _capi.ptr(row_pack), _capi.ptr(grad_rst), _capi.ptr(grad_ft),
-            _capi.ptr(grad_el), _capi.ptr(hub_rows), n_hub, thr, stream)
+            _capi.ptr(grad_el), hub, stream)
         _capi.check(rc, "dglb_gat_fused_bwd_src")
-        _capi.count_launch(1 + (1 if n_hub else 0))
+        _capi.count_launch(1 + hub_launches)
     return grad_ft, grad_el
 
 

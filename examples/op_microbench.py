@@ -1,0 +1,62 @@
+"""Per-op timing (CUDA events) of gspmm / gsddmm on a synthetic graph of a named dataset shape:
+algorithmic GB/s (SURVEY.md 8d gather model) and fraction of the measured HBM peak."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "dgl-0.5-benchmark_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+import dgl  # noqa: E402
+from dgl.data import synthetic  # noqa: E402
+from bench import spmm_bytes, sddmm_dot_bytes, measured_peak  # noqa: E402
+
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="ogbn-products")
+    ap.add_argument("--widths", default="64,100")
+    ap.add_argument("--degree", default="uniform")
+    ap.add_argument("--order", default="shuffled")
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    n, e, _, _ = synthetic.SHAPES[args.shape]
+    src, dst = synthetic.random_edges(n, n, e, seed=0, degree=args.degree, order=args.order)
+    g = dgl.graph((torch.from_numpy(src), torch.from_numpy(dst)), num_nodes=n).int().to(dev)
+    peak, _ = measured_peak()
+    p = 0 if args.order == "dst_sorted" else 1
+    for D in [int(x) for x in args.widths.split(",")]:
+        X, V = torch.rand(n, D, device=dev), torch.rand(n, D, device=dev)
+        W = torch.rand(e, 1, device=dev)
+        res = {"shape": args.shape, "nodes": n, "edges": e, "D": D, "degree": args.degree, "order": args.order}
+        for name, fn, B in (
+                ("copy_u_sum", lambda: dgl.ops.gspmm(g, "copy_lhs", "sum", X, None), spmm_bytes(n, e, D)),
+                ("copy_u_mean", lambda: dgl.ops.gspmm(g, "copy_lhs", "mean", X, None), spmm_bytes(n, e, D)),
+                ("copy_u_max", lambda: dgl.ops.gspmm(g, "copy_lhs", "max", X, None), spmm_bytes(n, e, D) + 8 * D * n),
+                ("u_mul_e_sum(E,1)", lambda: dgl.ops.gspmm(g, "mul", "sum", X, W), spmm_bytes(n, e, D) + 4 * e + 4 * p * e),
+                ("u_dot_v", lambda: dgl.ops.gsddmm(g, "dot", X, V), sddmm_dot_bytes(n, e, D, p=p))):
+            ms = timeit(fn)
+            res[name] = {"ms": round(ms, 4), "gbs": round(B / ms / 1e6), "frac": round(B / ms / 1e6 / peak, 3)}
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,8 +24,8 @@
  *   - return value: 0 = ok, negative = DGLB_E_* below; dglb_last_error() gives the
  *     message for the calling thread.
  *   - the library holds no per-graph state.  The only per-graph metadata is the
- *     caller-owned "hub row" list (rows whose nnz exceeds a threshold) produced by
- *     dglb_csr_find_hub_rows().
+ *     caller-owned "hub row" description dglb_hub_t (rows whose nnz exceeds a threshold, produced by
+ *     dglb_csr_find_hub_rows(), cut into segments of bounded length).
  */
 #ifndef DGLB200_H_
 #define DGLB200_H_
@@ -110,6 +110,27 @@ int dglb_csr_find_hub_rows(int64_t n_rows, const int32_t* indptr, int32_t thresh
 /* threshold the library recommends for a given feature width (elements) */
 int32_t dglb_default_hub_threshold(int64_t out_len);
 
+/* Hub-row metadata handed to the compute entry points (NULL = treat every row as an ordinary row).
+ * Rows with nnz > threshold are skipped by the row-per-group kernels.  gspmm / gsddmm cut each hub
+ * row into segments of at most seg_len entries, one CTA per segment, so a 20 000-edge hub is spread
+ * over many SMs; gspmm writes per-segment partial results to `workspace` and a second kernel
+ * combines the segments of a row in segment order (deterministic, no atomics; max/min ties still
+ * resolve to the first CSR entry).  edge_softmax and the fused GAT kernels use one CTA per hub row.
+ *   rows     [n_hub]    hub row ids
+ *   seg_ptr  [n_hub+1]  first segment of each hub row (prefix sum of ceil(nnz/seg_len))
+ *   seg_hub  [n_seg]    index into rows[] of the hub row a segment belongs to
+ *   workspace           device scratch of >= dglb_hub_workspace_bytes(n_seg, out_len, with_args)
+ * All arrays are device pointers owned by the caller. */
+typedef struct dglb_hub_t {
+  const int32_t* rows;
+  const int32_t* seg_ptr;
+  const int32_t* seg_hub;
+  int32_t n_hub, n_seg, seg_len, threshold;
+  void* workspace;
+  size_t workspace_bytes;
+} dglb_hub_t;
+size_t dglb_hub_workspace_bytes(int64_t n_seg, int64_t out_len, int with_args);
+
 /* ---------------------------------------------------------------- generalized SpMM
  * replaces upstream FFI `_CAPI_DGLKernelSpMM` (src/array/kernel.cc::SpMM ->
  * cuda/spmm.cu::SpMMCsr / CusparseCsrmm2 / cuda/spmm.cuh::SpMMCsrKernel).
@@ -128,9 +149,9 @@ int32_t dglb_default_hub_threshold(int64_t out_len);
  *    used for reducer "mean" with row_scale = float(clamp(in_deg,1)).
  *  - accumulate != 0 (reducer sum only): out[r,:] += result instead of out[r,:] = result; lets a
  *    row-partitioned caller aggregate one source shard at a time while the next shard is in flight.
- *  - hub_rows/n_hub (may be NULL/0): rows listed there (nnz > hub_threshold) are processed by
- *    the split-row path (one CTA per row) instead of the row-per-group path; the list must
- *    come from dglb_csr_find_hub_rows(indptr, hub_threshold).
+ *  - hub (may be NULL): rows listed there (nnz > hub->threshold) are processed by the segmented
+ *    split-row path instead of the row-per-group path; the list must come from
+ *    dglb_csr_find_hub_rows(indptr, hub->threshold).
  */
 int dglb_gspmm_csr(int op, int reduce, int dtype,
                    int64_t n_rows, int64_t n_cols, int64_t nnz,
@@ -139,7 +160,7 @@ int dglb_gspmm_csr(int op, int reduce, int dtype,
                    int ndim, const int64_t* lhs_shape_host, const int64_t* rhs_shape_host,
                    void* out, int32_t* arg_u, int32_t* arg_e,
                    const float* row_scale, int accumulate,
-                   const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
+                   const dglb_hub_t* hub,
                    void* stream);
 
 /* ---------------------------------------------------------------- generalized SDDMM
@@ -162,7 +183,7 @@ int dglb_gsddmm_csr(int op, int dtype, int lhs_target, int rhs_target,
                     const void* lhs, const void* rhs,
                     int ndim, const int64_t* lhs_shape_host, const int64_t* rhs_shape_host,
                     void* out,
-                    const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
+                    const dglb_hub_t* hub,
                     void* stream);
 
 int dglb_gsddmm_coo(int op, int dtype, int lhs_target, int rhs_target,
@@ -182,12 +203,12 @@ int dglb_gsddmm_coo(int op, int dtype, int lhs_target, int rhs_target,
 int dglb_edge_softmax_fwd(int dtype, int64_t n_dst, int64_t nnz, int64_t n_heads,
                           const int32_t* indptr, const int32_t* eids,
                           const void* logits, void* out,
-                          const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
+                          const dglb_hub_t* hub,
                           void* stream);
 int dglb_edge_softmax_bwd(int dtype, int64_t n_dst, int64_t nnz, int64_t n_heads,
                           const int32_t* indptr, const int32_t* eids,
                           const void* out, const void* grad_out, void* grad_logits,
-                          const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
+                          const dglb_hub_t* hub,
                           void* stream);
 
 /* ---------------------------------------------------------------- fused GAT attention
@@ -216,7 +237,7 @@ int dglb_gat_fused_fwd(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz,
                        const void* ft, const void* el, const void* er,
                        void* rst, float* row_max, float* row_sum,
                        void* edge_scores,
-                       const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
+                       const dglb_hub_t* hub,
                        void* stream);
 
 int dglb_gat_fused_bwd_dst(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz,
@@ -227,7 +248,7 @@ int dglb_gat_fused_bwd_dst(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz,
                            const float* row_max, const float* row_sum,
                            const void* grad_rst,
                            float* row_pack /* (n_dst,H,4), 16-byte aligned */, void* grad_er /* (n_dst,H) */,
-                           const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
+                           const dglb_hub_t* hub,
                            void* stream);
 
 int dglb_gat_fused_bwd_src(int dtype, int64_t n_src, int64_t n_dst, int64_t nnz,
@@ -239,7 +260,7 @@ int dglb_gat_fused_bwd_src(int dtype, int64_t n_src, int64_t n_dst, int64_t nnz,
                            const float* row_pack /* from _bwd_dst */,
                            const void* grad_rst,
                            void* grad_ft /* (n_src,H,F) */, void* grad_el /* (n_src,H) */,
-                           const int32_t* hub_rows, int32_t n_hub, int32_t hub_threshold,
+                           const dglb_hub_t* hub,
                            void* stream);
 
 #ifdef __cplusplus

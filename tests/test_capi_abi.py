@@ -58,7 +58,7 @@ def test_argument_errors_are_reported_without_a_gpu(built_lib):
     shp = _capi.shape_arr((4,))
     # unknown op -> DGLB_E_INVALID before any CUDA call
     rc = l.dglb_gspmm_csr(99, 0, 0, 1, 1, 0, None, None, None, None, None, 1, shp, shp, None, None, None, None,
-                          0, None, 0, 0, None)
+                          0, None, None)
     assert rc == -1 and b"unknown op" in l.dglb_last_error()
     bad = _capi.shape_arr((3,))
     rc = l.dglb_gsddmm_coo(0, 0, 0, 2, 1, 1, 1, None, None, ctypes.c_void_p(8), ctypes.c_void_p(8), 1, shp, bad,

@@ -48,7 +48,12 @@ def test_empty_graph_and_isolated_nodes(oracle, cuda):
 def test_hub_row_list(oracle, cuda):
     og, g, src, dst = graphs(oracle, 2000, 2000, 60000, seed=3, kind="powerlaw")
     deg = og.in_degrees()
-    rows, cnt = g._graph.csc().hubs(100)
+    info = g._graph.csc().hubs(100)
     want = np.nonzero(deg > 100)[0]
-    assert cnt == len(want) and cnt > 0
-    assert sorted(n(rows).tolist()) == want.tolist()
+    assert info.n_hub == len(want) and info.n_hub > 0
+    assert n(info.rows).tolist() == want.tolist()
+    nseg = -(-deg[want] // 100)
+    assert info.n_seg == nseg.sum() and info.seg_len == 100
+    assert n(info.seg_ptr).tolist() == [0] + np.cumsum(nseg).tolist()
+    assert n(info.seg_hub).tolist() == np.repeat(np.arange(len(want)), nseg).tolist()
+    assert g._graph.csc().hubs(10 ** 9) is None
