@@ -17,9 +17,10 @@ roofline= the dominant kernel (gspmm copy_u_sum, D=602): bytes / its average dur
 cpu_baseline / --impl reference = the CPU oracle (C/OpenMP restatement of DGL v0.6.1's CPU kernels;
           DGL itself cannot be installed here) on a bounded sample of the same workload.
 
-N > 1 (torchrun): every rank holds the whole graph structure and owns a contiguous, nnz-balanced
-range of destination rows (1-D row partition) and the matching rows of X; each op first all-gathers
-the source features over NCCL, then aggregates its own rows.  Total work is fixed: "strong".
+N > 1 (torchrun): every rank owns a contiguous, nnz-balanced range of destination rows (1-D row
+partition) and the matching rows of X; each operand is all-gathered over NCCL in equal-sized chunks
+straight into the padded buffer the kernels read and aggregated chunk by chunk behind its gather
+(dgl/distributed_rows.py).  Total work is fixed: "strong".
 """
 import argparse
 import json
