@@ -40,8 +40,8 @@ import numpy as np  # noqa: E402
 
 N_NODES, N_EDGES = 232965, 11606919
 # dram__bytes_read.sum + dram__bytes_write.sum of the D=602 gspmm launch, from the committed
-# `ncu --set full` capture (profiles/r01_ncu_full_summary.md): 26.74 GB + 0.58 GB
-TRAFFIC_D602 = 27317947784
+# `ncu --set full` capture (profiles/r01_ncu_d602_final.md): 26.69 GB + 0.58 GB
+TRAFFIC_D602 = 27263905440
 WIDTHS = (64, 128, 256, 602)
 METRIC = "gspmm copy_u_sum + gsddmm u_dot_v algorithmic HBM GB/s (reddit-shaped, D=64..602)"
 
