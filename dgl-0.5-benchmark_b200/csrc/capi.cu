@@ -95,11 +95,6 @@ int dglb_coo_to_csr(int64_t n_rows, int64_t nnz, const int32_t* row, const int32
                     static_cast<cudaStream_t>(stream));
 }
 
-int dglb_permute_rows(int64_t n, int64_t row_len, const int32_t* perm, const void* in, void* out, void* stream) {
-  DGLB_CHECK_ARG(n >= 0 && row_len >= 0 && (n == 0 || row_len == 0 || (perm && in && out)), "permute_rows: bad arguments");
-  return permute_rows(n, row_len, perm, in, out, static_cast<cudaStream_t>(stream));
-}
-
 int dglb_csr_degrees(int64_t n_rows, const int32_t* indptr, int32_t* deg, void* stream) {
   DGLB_CHECK_ARG(n_rows >= 0 && indptr && (deg || n_rows == 0), "csr_degrees: bad arguments");
   return csr_degrees(n_rows, indptr, deg, static_cast<cudaStream_t>(stream));

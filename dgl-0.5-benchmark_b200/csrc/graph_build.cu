@@ -58,15 +58,6 @@ __global__ void hub_rows_kernel(const int32_t* __restrict__ indptr, int64_t n_ro
   }
 }
 
-__global__ void permute_rows_kernel(const int32_t* __restrict__ perm, const uint32_t* __restrict__ in,
-                                    uint32_t* __restrict__ out, int64_t n, int row_len) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * row_len) return;
-  const int64_t j = idx / row_len;
-  const int k = (int)(idx - j * row_len);
-  out[idx] = __ldg(in + (int64_t)__ldg(perm + j) * row_len + k);
-}
-
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static int key_bits(int64_t n_rows) {
@@ -112,16 +103,6 @@ int coo_to_csr(int64_t n_rows, int64_t nnz, const int32_t* row, const int32_t* c
   DGLB_LAUNCH_CHECK("gather_cols_kernel");
   indptr_from_sorted_kernel<<<blocks, threads, 0, stream>>>(keys_out, indptr, nnz, n_rows);
   DGLB_LAUNCH_CHECK("indptr_from_sorted_kernel");
-  return DGLB_OK;
-}
-
-int permute_rows(int64_t n, int64_t row_len, const int32_t* perm, const void* in, void* out, cudaStream_t stream) {
-  if (n == 0 || row_len == 0) return DGLB_OK;
-  const int64_t blocks = (n * row_len + 255) / 256;
-  if (blocks > 0x7fffffffLL || row_len >= (1 << 30)) { set_error("permute_rows: problem too large"); return DGLB_E_UNSUPPORTED; }
-  permute_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(perm, static_cast<const uint32_t*>(in),
-                                                            static_cast<uint32_t*>(out), n, (int)row_len);
-  DGLB_LAUNCH_CHECK("permute_rows_kernel");
   return DGLB_OK;
 }
 

@@ -55,7 +55,6 @@ size_t coo_to_csr_workspace_bytes(int64_t n_rows, int64_t nnz);
 int coo_to_csr(int64_t n_rows, int64_t nnz, const int32_t* row, const int32_t* col, int32_t* indptr,
                int32_t* indices, int32_t* data, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int csr_degrees(int64_t n_rows, const int32_t* indptr, int32_t* deg, cudaStream_t stream);
-int permute_rows(int64_t n, int64_t row_len, const int32_t* perm, const void* in, void* out, cudaStream_t stream);
 int is_identity_perm(int64_t n, const int32_t* data, int32_t* flag, cudaStream_t stream);
 int csr_find_hub_rows(int64_t n_rows, const int32_t* indptr, int32_t threshold, int32_t* hub_rows,
                       int64_t cap, int32_t* n_hub, cudaStream_t stream);

@@ -47,7 +47,6 @@ _SIGNATURES = {
     "dglb_coo_to_csr_workspace_bytes": (ctypes.c_size_t, [_i64, _i64]),
     "dglb_coo_to_csr": (_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
     "dglb_csr_degrees": (_int, [_i64, _vp, _vp, _vp]),
-    "dglb_permute_rows": (_int, [_i64, _i64, _vp, _vp, _vp, _vp]),
     "dglb_is_identity_perm": (_int, [_i64, _vp, _vp, _vp]),
     "dglb_csr_find_hub_rows": (_int, [_i64, _vp, _i32, _vp, _i64, _vp, _vp]),
     "dglb_default_hub_threshold": (_i32, [_i64]),

@@ -15,9 +15,6 @@ from ._capi import DGLError
 
 _TARGET = _capi.TARGETS
 
-# Per-edge operands of at most this many bytes per edge are permuted into CSC order before the SpMM.
-NARROW_EDGE_BYTES = 32
-
 # Rows with more nnz than this are handled by the split-row ("hub") kernels.  None = the library's
 # width-dependent default (dglb_default_hub_threshold); tests lower it to exercise the hub path.
 HUB_THRESHOLD = None
@@ -146,18 +143,9 @@ def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None):
         hub, _keep, hub_launches = _hub_arg(csc.hubs(thr), dev, out_len, use_cmp)
         ndim, ls, rs = _shapes_for_abi(op, u, e)
         stream = _capi.enter(dev)
-        eids = csc.eids
-        if use_e and eids is not None and not use_cmp and e[0].numel() * 4 <= NARROW_EDGE_BYTES:
-            # narrow per-edge operand in edge-id order: one streaming permutation into CSC order, then
-            # the SpMM reads it coalesced (a scattered 4-byte gather per edge cost +50% at D=602)
-            e_csc = torch.empty_like(e)
-            _capi.check(l.dglb_permute_rows(csc.nnz, e[0].numel(), _capi.ptr(eids), _capi.ptr(e), _capi.ptr(e_csc),
-                                            stream), "dglb_permute_rows")
-            _capi.count_launch(1)
-            e, eids = e_csc, None
         rc = l.dglb_gspmm_csr(_capi.OPS[op], _capi.REDUCERS[reduce_op], _capi.F32,
                               csc.n_rows, csc.n_cols, csc.nnz,
-                              _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(eids),
+                              _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(csc.eids),
                               _capi.ptr(u), _capi.ptr(e), ndim, ls, rs,
                               _capi.ptr(v), _capi.ptr(arg_u), _capi.ptr(arg_e), _capi.ptr(row_scale),
                               1 if out is not None else 0, hub, stream)

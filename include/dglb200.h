@@ -131,12 +131,6 @@ typedef struct dglb_hub_t {
 } dglb_hub_t;
 size_t dglb_hub_workspace_bytes(int64_t n_seg, int64_t out_len, int with_args);
 
-/* out[j, :] = in[perm[j], :] for j < n, rows of row_len 32-bit words (any 4-byte dtype).  Layout
- * pre-pass: narrow per-edge operands (scalar / per-head edge weights) stored in edge-id order are
- * brought into CSC order once so the SpMM reads them coalesced with the column indices instead of
- * issuing a scattered 4-byte gather per edge. */
-int dglb_permute_rows(int64_t n, int64_t row_len, const int32_t* perm, const void* in, void* out, void* stream);
-
 /* ---------------------------------------------------------------- generalized SpMM
  * replaces upstream FFI `_CAPI_DGLKernelSpMM` (src/array/kernel.cc::SpMM ->
  * cuda/spmm.cu::SpMMCsr / CusparseCsrmm2 / cuda/spmm.cuh::SpMMCsrKernel).
