@@ -179,3 +179,24 @@ def test_hub_rows_u_mul_e_and_copy_e(oracle, cuda, shape, small_hub_threshold):
             assert_close_sumscaled(got, want, abs_sum_scale_spmm(src, dst, 2000, np.abs(We)), rtol=1e-5, what="hub copy_e")
         else:
             assert np.array_equal(got, want)
+
+
+def test_int64_graph_ids_and_noncontiguous_inputs(oracle, cuda):
+    """Graphs that were not cast with .int() keep idtype int64 at the API (arg outputs included);
+    non-contiguous feature views are accepted."""
+    from dgl import sparse as K
+    og, g, src, dst = graphs(oracle, 120, 120, 2000, seed=12)
+    g64 = g.long()
+    assert g64.idtype == torch.int64 and g64.edges()[0].dtype == torch.int64
+    X = np.random.default_rng(12).random((120, 24), dtype=np.float32)
+    Xt = t(X)
+    assert np.array_equal(n(dgl.ops.gspmm(g64, "copy_lhs", "sum", Xt, None)), oracle.gspmm(og, "copy_lhs", "sum", X, None))
+    out, (au, _) = K._gspmm(g64._graph, "copy_lhs", "max", Xt, None)
+    assert au.dtype == torch.int64
+    want, (wu, _) = oracle.gspmm_with_args(og, "copy_lhs", "max", X, None)
+    assert np.array_equal(n(au), wu)
+    view = t(np.concatenate([X, X], 1))[:, ::2]                      # strided view
+    assert not view.is_contiguous()
+    got = n(dgl.ops.gspmm(g, "copy_lhs", "sum", view, None))
+    assert np.array_equal(got, oracle.gspmm(og, "copy_lhs", "sum", n(view), None))
+    assert np.array_equal(n(dgl.ops.gsddmm(g64, "dot", Xt, Xt)), n(dgl.ops.gsddmm(g, "dot", Xt, Xt)))

@@ -144,3 +144,18 @@ def test_synthetic_generator_is_seeded_and_shaped():
     assert np.all(np.diff(d) >= 0)
     n, s, d = synthetic.shaped_edges("cora", self_loops=True)
     assert n == 2708 and len(s) == 10556 + 2708 and np.array_equal(s[-2708:], np.arange(2708))
+
+
+def test_bench_byte_model_matches_survey_appendix_c():
+    """bench.py's algorithmic-byte formulas reproduce SURVEY.md Appendix C (reddit 11.6 M edges)."""
+    import importlib.util, os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    n, e = 232965, 11606919
+    assert abs(bench.spmm_bytes(n, e, 64) / 1e9 - 3.08) < 0.01
+    assert abs(bench.spmm_bytes(n, e, 602) / 1e9 - 28.56) < 0.01
+    assert abs(bench.sddmm_dot_bytes(n, e, 602, p=0) / 1e9 - 28.6) < 0.1
+    assert bench.spmm_bytes(n, e, 602) // e == 2460            # 2 460 B per edge (SURVEY 8d)
+    assert abs(bench.step_bytes(n, e) / 1e9 - 100.2) < 0.2
