@@ -132,7 +132,7 @@ int dglb_gspmm_csr(int op, int reduce, int dtype, int64_t n_rows, int64_t n_cols
                    const dglb_hub_t* hub, void* stream) {
   DGLB_CHECK_ARG(valid_op(op, false), "gspmm: unknown op %d", op);
   DGLB_CHECK_ARG(reduce >= DGLB_REDUCE_SUM && reduce <= DGLB_REDUCE_MIN, "gspmm: unknown reducer %d", reduce);
-  if (dtype != DGLB_F32) { set_error("gspmm: only f32 is implemented (dtype=%d)", dtype); return DGLB_E_UNSUPPORTED; }
+  if (dtype != DGLB_F32 && dtype != DGLB_BF16) { set_error("gspmm: unknown dtype %d", dtype); return DGLB_E_UNSUPPORTED; }
   DGLB_CHECK_ARG(n_rows >= 0 && n_cols >= 0 && nnz >= 0, "gspmm: negative size");
   DGLB_CHECK_ARG(indptr && (indices || nnz == 0) && out, "gspmm: null graph/out pointer");
   DGLB_CHECK_ARG(op == DGLB_OP_COPY_RHS || ufeat || nnz == 0, "gspmm: op needs lhs (node) data");
@@ -144,6 +144,9 @@ int dglb_gspmm_csr(int op, int reduce, int dtype, int64_t n_rows, int64_t n_cols
   if (rc != DGLB_OK) return rc;
   if (op == DGLB_OP_COPY_LHS) { for (int d = 0; d < b.ndim; ++d) { b.rhs[d] = b.lhs[d]; b.out[d] = b.lhs[d]; } b.rhs_len = b.out_len = b.lhs_len; }
   if (op == DGLB_OP_COPY_RHS) { for (int d = 0; d < b.ndim; ++d) { b.lhs[d] = b.rhs[d]; b.out[d] = b.rhs[d]; } b.lhs_len = b.out_len = b.rhs_len; }
+  if (dtype == DGLB_BF16)
+    return spmm_csr_bf16(op, reduce, n_rows, indptr, indices, ufeat, b.out_len, out, row_scale, accumulate, hub,
+                         static_cast<cudaStream_t>(stream));
   return spmm_csr_f32(op, reduce, n_rows, n_cols, nnz, indptr, indices, eids, static_cast<const float*>(ufeat),
                       static_cast<const float*>(efeat), b, static_cast<float*>(out), arg_u, arg_e, row_scale,
                       accumulate, hub, static_cast<cudaStream_t>(stream));
@@ -153,7 +156,7 @@ static int sddmm_common(int op, int dtype, int lhs_target, int rhs_target, int n
                         const int64_t* rs_, const void* lhs, const void* rhs, void* out, int64_t nnz,
                         BcastShape* b, int64_t* reduce_size) {
   DGLB_CHECK_ARG(valid_op(op, true), "gsddmm: unknown op %d", op);
-  if (dtype != DGLB_F32) { set_error("gsddmm: only f32 is implemented (dtype=%d)", dtype); return DGLB_E_UNSUPPORTED; }
+  if (dtype != DGLB_F32 && dtype != DGLB_BF16) { set_error("gsddmm: unknown dtype %d", dtype); return DGLB_E_UNSUPPORTED; }
   DGLB_CHECK_ARG(lhs_target >= 0 && lhs_target <= 2 && rhs_target >= 0 && rhs_target <= 2, "gsddmm: bad target");
   DGLB_CHECK_ARG(nnz >= 0 && (out || nnz == 0), "gsddmm: bad nnz/out");
   DGLB_CHECK_ARG(op == DGLB_OP_COPY_RHS || lhs || nnz == 0, "gsddmm: op needs lhs data");
@@ -179,8 +182,12 @@ int dglb_gsddmm_csr(int op, int dtype, int lhs_target, int rhs_target, int64_t n
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (lhs_target == DGLB_TARGET_U && rhs_target == DGLB_TARGET_V) {
     rc = sddmm_csr_fast_f32(op, n_dst, indptr, indices, eids, static_cast<const float*>(lhs),
-                            static_cast<const float*>(rhs), b, rs, static_cast<float*>(out), hub, st);
+                            static_cast<const float*>(rhs), b, rs, static_cast<float*>(out), hub, st, dtype);
     if (rc != DGLB_E_UNSUPPORTED) return rc;
+  }
+  if (dtype != DGLB_F32) {
+    set_error("gsddmm: bf16 storage is implemented for u_dot_v on the CSC (single head or power-of-two head segments)");
+    return DGLB_E_UNSUPPORTED;
   }
   GenericSddmmParams g;
   g.src = nullptr; g.dst = nullptr; g.indptr = indptr; g.indices = indices; g.eids = eids;
@@ -199,6 +206,7 @@ int dglb_gsddmm_coo(int op, int dtype, int lhs_target, int rhs_target, int64_t n
   int rc = sddmm_common(op, dtype, lhs_target, rhs_target, ndim, lhs_shape_host, rhs_shape_host, lhs, rhs, out, nnz, &b, &rs);
   if (rc != DGLB_OK) return rc;
   DGLB_CHECK_ARG((src && dst) || nnz == 0, "gsddmm_coo: null src/dst");
+  if (dtype != DGLB_F32) { set_error("gsddmm_coo: only f32 is implemented"); return DGLB_E_UNSUPPORTED; }
   if (nnz == 0) return DGLB_OK;
   GenericSddmmParams g;
   g.src = src; g.dst = dst; g.indptr = nullptr; g.indices = nullptr; g.eids = nullptr;

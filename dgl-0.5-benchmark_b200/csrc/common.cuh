@@ -1,5 +1,6 @@
 // common.cuh -- shared helpers for the sm_100a sparse message-passing kernels.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -81,6 +82,68 @@ __device__ __forceinline__ void st_vec_i32(int32_t* p, const int32_t (&r)[VEC]) 
   }
 }
 
+// ------------------------------------------------------------------ typed rows: fp32 or bf16 storage
+// bf16 storage, fp32 arithmetic: VEC elements per access = 2*VEC bytes (VEC = 8 -> one 128-bit load).
+__device__ __forceinline__ float bf16lo(uint32_t x) { return __uint_as_float(x << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);  // round-to-nearest-even, .x = low half
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ FVec<VEC> ldg_vec_t(const T* p) {
+  if constexpr (sizeof(T) == 4) {
+    static_assert(VEC <= 4, "fp32 rows use at most 128-bit accesses");
+    return ldg_vec<VEC>(reinterpret_cast<const float*>(p));
+  } else {
+    FVec<VEC> r;
+    if constexpr (VEC == 8) {
+      const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+      r.v[0] = bf16lo(t.x); r.v[1] = bf16hi(t.x); r.v[2] = bf16lo(t.y); r.v[3] = bf16hi(t.y);
+      r.v[4] = bf16lo(t.z); r.v[5] = bf16hi(t.z); r.v[6] = bf16lo(t.w); r.v[7] = bf16hi(t.w);
+    } else if constexpr (VEC == 4) {
+      const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+      r.v[0] = bf16lo(t.x); r.v[1] = bf16hi(t.x); r.v[2] = bf16lo(t.y); r.v[3] = bf16hi(t.y);
+    } else if constexpr (VEC == 2) {
+      const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(p));
+      r.v[0] = bf16lo(t); r.v[1] = bf16hi(t);
+    } else {
+      r.v[0] = bf16lo((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)));
+    }
+    return r;
+  }
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void st_vec_t(T* p, const FVec<VEC>& r) {
+  if constexpr (sizeof(T) == 4) {
+    st_vec<VEC>(reinterpret_cast<float*>(p), r);
+  } else {
+    if constexpr (VEC == 8) {
+      *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(r.v[0], r.v[1]), pack_bf16x2(r.v[2], r.v[3]),
+                                               pack_bf16x2(r.v[4], r.v[5]), pack_bf16x2(r.v[6], r.v[7]));
+    } else if constexpr (VEC == 4) {
+      *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(r.v[0], r.v[1]), pack_bf16x2(r.v[2], r.v[3]));
+    } else if constexpr (VEC == 2) {
+      *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(r.v[0], r.v[1]);
+    } else {
+      *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(r.v[0]);
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ float load_scalar_t(const T* p) {
+  if constexpr (sizeof(T) == 4) return *reinterpret_cast<const float*>(p);
+  else return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p));
+}
+template <typename T>
+__device__ __forceinline__ void store_scalar_t(T* p, float v) {
+  if constexpr (sizeof(T) == 4) *reinterpret_cast<float*>(p) = v;
+  else *reinterpret_cast<__nv_bfloat16*>(p) = __float2bfloat16_rn(v);
+}
+
 // ------------------------------------------------------------------ host-side launch geometry
 // Lanes per row ("group"): the smallest power of two >= ncols (vector columns), capped at 32.
 inline int group_lanes(int64_t ncols) {
@@ -94,6 +157,15 @@ inline int pick_vec(int64_t len, const void* ptr) {
   uintptr_t a = reinterpret_cast<uintptr_t>(ptr);
   if (len % 4 == 0 && a % 16 == 0) return 4;
   if (len % 2 == 0 && a % 8 == 0) return 2;
+  return 1;
+}
+
+// bf16 rows: widest element count per access out of {8,4,2,1} (16/8/4/2 bytes)
+inline int pick_vec_bf16(int64_t len, const void* ptr) {
+  uintptr_t a = reinterpret_cast<uintptr_t>(ptr);
+  if (len % 8 == 0 && a % 16 == 0) return 8;
+  if (len % 4 == 0 && a % 8 == 0) return 4;
+  if (len % 2 == 0 && a % 4 == 0) return 2;
   return 1;
 }
 

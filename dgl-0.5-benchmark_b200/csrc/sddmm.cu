@@ -111,7 +111,7 @@ __host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x
 // LOGG >= 0: single output column, G = 2^LOGG known at compile time (transposing reduction).
 // LOGG == -1: (N,H,F) operands, runtime G and `seg` lanes per head (segmented butterfly).
 // SINGLE: the whole row fits one feature tile, so the destination row lives in registers.
-template <int VEC, int CH, int LOGG, bool SINGLE, bool HUB>
+template <int VEC, int CH, int LOGG, bool SINGLE, bool HUB, typename T = float>
 __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmParams p) {
   constexpr int U = 8 / CH;
   const int G = LOGG >= 0 ? (1 << LOGG) : p.G;
@@ -121,13 +121,15 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmPar
   group_work<HUB>(p, row, j0, n);
   const int nmax = __reduce_max_sync(FULL_MASK, n);
   const int tile_cols = G * CH;
-  const float* __restrict__ vrow = p.V + row * (int64_t)p.D;
+  const T* __restrict__ vrow = reinterpret_cast<const T*>(p.V) + row * (int64_t)p.D;
+  const T* __restrict__ ubase = reinterpret_cast<const T*>(p.U);
+  T* __restrict__ obase = reinterpret_cast<T*>(p.out);
   FVec<VEC> vreg[CH];
   if constexpr (SINGLE) {
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int vc = c * G + lg;
-      if (n > 0 && vc < p.ncols) vreg[c] = ldg_vec<VEC>(vrow + vc * VEC);
+      if (n > 0 && vc < p.ncols) vreg[c] = ldg_vec_t<T, VEC>(vrow + vc * VEC);
     }
   }
   for (int off = 0; off < nmax; off += G) {
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmPar
           const int vc = tile0 + c * G + lg;
           colv[c] = vc < p.ncols;
           if constexpr (!SINGLE) {
-            if (colv[c] && m > 0) vv[c] = ldg_vec<VEC>(vrow + vc * VEC);
+            if (colv[c] && m > 0) vv[c] = ldg_vec_t<T, VEC>(vrow + vc * VEC);
           }
         }
 #pragma unroll
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmPar
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             if ((t + u) < m && colv[c])
-              xv[u][c] = ldg_vec<VEC>(p.U + (int64_t)cc[u] * p.D + (tile0 + c * G + lg) * VEC);
+              xv[u][c] = ldg_vec_t<T, VEC>(ubase + (int64_t)cc[u] * p.D + (tile0 + c * G + lg) * VEC);
           }
         }
         // phase 2: multiply-accumulate
@@ -187,14 +189,14 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmPar
         if constexpr (GG >= U) {
           const int u_l = lg >> (LOGG - ilog2(U));
           const int e = __shfl_sync(FULL_MASK, my_e, t + u_l, GG);
-          if ((lg & (GG / U - 1)) == 0 && (t + u_l) < m) p.out[e] = part[0];
+          if ((lg & (GG / U - 1)) == 0 && (t + u_l) < m) store_scalar_t<T>(obase + e, part[0]);
         } else {
           constexpr int CF = U / GG;
 #pragma unroll
           for (int i = 0; i < CF; ++i) {
             const int u_l = lg * CF + i;
             const int e = __shfl_sync(FULL_MASK, my_e, t + u_l, GG);
-            if ((t + u_l) < m) p.out[e] = part[i];
+            if ((t + u_l) < m) store_scalar_t<T>(obase + e, part[i]);
           }
         }
       } else {
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmPar
           const int e = __shfl_sync(FULL_MASK, my_e, t + u, G);
           for (int s = p.seg >> 1; s > 0; s >>= 1) part[u] += __shfl_xor_sync(FULL_MASK, part[u], s);
           if ((t + u) < m && (lg & (p.seg - 1)) == 0 && (lg / p.seg) < p.H)
-            p.out[(int64_t)e * p.H + (lg / p.seg)] = part[u];
+            store_scalar_t<T>(obase + (int64_t)e * p.H + (lg / p.seg), part[u]);
         }
       }
     }
@@ -346,37 +348,42 @@ int sddmm_generic_f32(const GenericSddmmParams& g, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------ dispatch
-template <int VEC, int CH, int LOGG, bool SINGLE>
+template <int VEC, int CH, int LOGG, bool SINGLE, typename T>
 static int launch_dot(const SddmmParams& p, int n_hub, cudaStream_t stream) {
   const int rows_per_block = kBlockThreads / p.G;
   const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
   if (blocks > 0) {
-    sddmm_dot_kernel<VEC, CH, LOGG, SINGLE, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+    sddmm_dot_kernel<VEC, CH, LOGG, SINGLE, false, T><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
     DGLB_LAUNCH_CHECK("sddmm_dot_kernel");
   }
   if (n_hub > 0) {
-    sddmm_dot_kernel<VEC, CH, LOGG, SINGLE, true><<<n_hub, kBlockThreads, 0, stream>>>(p);
+    sddmm_dot_kernel<VEC, CH, LOGG, SINGLE, true, T><<<n_hub, kBlockThreads, 0, stream>>>(p);
     DGLB_LAUNCH_CHECK("sddmm_dot_kernel(hub)");
   }
   return DGLB_OK;
 }
 
-template <int VEC>
+template <int VEC, typename T = float>
 static int dispatch_dot(const SddmmParams& p, int ch, int n_hub, cudaStream_t stream) {
   const bool single = p.ncols <= p.G * ch;
-  if (p.H > 1) return launch_dot<VEC, 1, -1, true>(p, n_hub, stream);  // caller guarantees ch == 1
+  if (p.H > 1) return launch_dot<VEC, 1, -1, true, T>(p, n_hub, stream);  // caller guarantees ch == 1
   if (ch == 1) {
     switch (p.log2G) {
-      case 0: return launch_dot<VEC, 1, 0, true>(p, n_hub, stream);
-      case 1: return launch_dot<VEC, 1, 1, true>(p, n_hub, stream);
-      case 2: return launch_dot<VEC, 1, 2, true>(p, n_hub, stream);
-      case 3: return launch_dot<VEC, 1, 3, true>(p, n_hub, stream);
-      case 4: return launch_dot<VEC, 1, 4, true>(p, n_hub, stream);
-      default: return launch_dot<VEC, 1, 5, true>(p, n_hub, stream);
+      case 0: return launch_dot<VEC, 1, 0, true, T>(p, n_hub, stream);
+      case 1: return launch_dot<VEC, 1, 1, true, T>(p, n_hub, stream);
+      case 2: return launch_dot<VEC, 1, 2, true, T>(p, n_hub, stream);
+      case 3: return launch_dot<VEC, 1, 3, true, T>(p, n_hub, stream);
+      case 4: return launch_dot<VEC, 1, 4, true, T>(p, n_hub, stream);
+      default: return launch_dot<VEC, 1, 5, true, T>(p, n_hub, stream);
     }
   }
-  if (ch == 2) return single ? launch_dot<VEC, 2, 5, true>(p, n_hub, stream) : launch_dot<VEC, 2, 5, false>(p, n_hub, stream);
-  return single ? launch_dot<VEC, 4, 5, true>(p, n_hub, stream) : launch_dot<VEC, 4, 5, false>(p, n_hub, stream);
+  if (ch == 2)
+    return single ? launch_dot<VEC, 2, 5, true, T>(p, n_hub, stream) : launch_dot<VEC, 2, 5, false, T>(p, n_hub, stream);
+  if constexpr (VEC < 8) {
+    return single ? launch_dot<VEC, 4, 5, true, T>(p, n_hub, stream) : launch_dot<VEC, 4, 5, false, T>(p, n_hub, stream);
+  } else {
+    return DGLB_E_UNSUPPORTED;  // VEC = 8 keeps CH <= 2 (register budget)
+  }
 }
 
 template <int VEC, int CH, int OP>
@@ -407,7 +414,8 @@ static int dispatch_ew(const SddmmParams& p, int vec, int ch, int n_hub, cudaStr
 // returns DGLB_E_UNSUPPORTED (without setting an error) when the vector path does not apply
 int sddmm_csr_fast_f32(int op, int64_t n_dst, const int32_t* indptr, const int32_t* indices,
                        const int32_t* eids, const float* Uf, const float* Vf, const BcastShape& b,
-                       int64_t reduce_size, float* out, const dglb_hub_t* hub, cudaStream_t stream) {
+                       int64_t reduce_size, float* out, const dglb_hub_t* hub, cudaStream_t stream, int dtype) {
+  if (dtype == DGLB_BF16 && op != DGLB_OP_DOT) return DGLB_E_UNSUPPORTED;
   if (b.lhs_len != b.rhs_len) return DGLB_E_UNSUPPORTED;
   for (int d = 0; d < b.ndim; ++d)
     if (b.lhs[d] != b.rhs[d]) return DGLB_E_UNSUPPORTED;
@@ -424,9 +432,13 @@ int sddmm_csr_fast_f32(int op, int64_t n_dst, const int32_t* indptr, const int32
   p.n_rows = n_dst; p.D = (int)D;
   p.hub_threshold = use_hub ? hub->threshold : INT32_MAX;
   const int n_hub = use_hub ? hub->n_seg : 0;  // hub launches are sized by SEGMENTS
-  int vec = 4;
-  if (op != DGLB_OP_COPY_RHS) vec = min_int(vec, pick_vec(D, Uf));
-  if (op != DGLB_OP_COPY_LHS) vec = min_int(vec, pick_vec(D, Vf));
+  int vec = dtype == DGLB_BF16 ? 8 : 4;
+  if (dtype == DGLB_BF16) {
+    vec = min_int(pick_vec_bf16(D, Uf), pick_vec_bf16(D, Vf));
+  } else {
+    if (op != DGLB_OP_COPY_RHS) vec = min_int(vec, pick_vec(D, Uf));
+    if (op != DGLB_OP_COPY_LHS) vec = min_int(vec, pick_vec(D, Vf));
+  }
   if (op == DGLB_OP_DOT) {
     const int64_t H = b.out_len;
     if (H > 1) {
@@ -448,9 +460,15 @@ int sddmm_csr_fast_f32(int op, int64_t n_dst, const int32_t* indptr, const int32
   while ((1 << p.log2G) < p.G) ++p.log2G;
   if (op == DGLB_OP_DOT && p.H == 1) p.seg = p.G;
   const int per_lane = (p.ncols + p.G - 1) / p.G;
-  const int ch = per_lane >= 4 ? 4 : (per_lane >= 2 ? 2 : 1);
+  const int ch = per_lane >= 4 ? (vec == 8 ? 2 : 4) : (per_lane >= 2 ? 2 : 1);
   if (op == DGLB_OP_DOT) {
     if (p.H > 1 && ch != 1) return DGLB_E_UNSUPPORTED;
+    if (dtype == DGLB_BF16) {
+      if (vec == 8) return dispatch_dot<8, __nv_bfloat16>(p, ch, n_hub, stream);
+      if (vec == 4) return dispatch_dot<4, __nv_bfloat16>(p, ch, n_hub, stream);
+      if (vec == 2) return dispatch_dot<2, __nv_bfloat16>(p, ch, n_hub, stream);
+      return dispatch_dot<1, __nv_bfloat16>(p, ch, n_hub, stream);
+    }
     if (vec == 4) return dispatch_dot<4>(p, ch, n_hub, stream);
     if (vec == 2) return dispatch_dot<2>(p, ch, n_hub, stream);
     return dispatch_dot<1>(p, ch, n_hub, stream);

@@ -91,9 +91,10 @@ __device__ __forceinline__ void combine(float& acc, int32_t& au, int32_t& ae, fl
 // Accumulate CSR positions [j0, j0+n) into `acc` for the feature tile starting at vector column
 // `tile0`.  n is uniform within the group, nmax is the warp-wide maximum of n so every lane of
 // the warp runs the same trip count (shuffles stay converged; extra trips are predicated off).
-template <int VEC, int CH, int OP, int RED, int RMODE>
+template <int VEC, int CH, int OP, int RED, int RMODE, typename T = float>
 __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0, int n, int nmax,
                                                  int lg, int tile0, Acc<VEC, CH, RED>& acc) {
+  static_assert(sizeof(T) == 4 || RMODE == RMODE_NONE, "bf16 storage is implemented for copy_lhs");
   constexpr int U = 8 / CH;
   constexpr bool USE_L = OP != DGLB_OP_COPY_RHS;
   constexpr bool USE_R = OP != DGLB_OP_COPY_LHS;
@@ -120,7 +121,7 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0
     for (int t = 0; t < mmax; t += U) {
       int cc[U], ee[U];
       FVec<VEC> xv[U][CH];
-      FVec<VEC> wv[U][CH];
+      FVec<(VEC > 4 ? 4 : VEC)> wv[U][CH];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         cc[u] = __shfl_sync(FULL_MASK, my_c, t + u, G);
@@ -132,9 +133,10 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           if (valid && colv[c]) {
-            if constexpr (USE_L) xv[u][c] = ldg_vec<VEC>(p.X + (int64_t)cc[u] * p.D + k[c]);
+            if constexpr (USE_L)
+              xv[u][c] = ldg_vec_t<T, VEC>(reinterpret_cast<const T*>(p.X) + (int64_t)cc[u] * p.D + k[c]);
             if constexpr (RMODE == RMODE_FULL)
-              wv[u][c] = ldg_vec<VEC>(p.W + (int64_t)ee[u] * p.D + k[c]);
+              wv[u][c] = ldg_vec_t<float, (VEC > 4 ? 4 : VEC)>(p.W + (int64_t)ee[u] * p.D + k[c]);
             if constexpr (RMODE == RMODE_HEAD)
               wv[u][c].v[0] = __ldg(p.W + (int64_t)ee[u] * p.rhs_len + hk[c]);
           }
@@ -168,7 +170,7 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0
 }
 
 // ------------------------------------------------------------------ row-per-group kernel
-template <int VEC, int CH, int OP, int RED, int RMODE>
+template <int VEC, int CH, int OP, int RED, int RMODE, typename T = float>
 __global__ void __launch_bounds__(kBlockThreads)
 spmm_rows_kernel(const SpmmParams p) {
   const int G = p.G;
@@ -187,7 +189,7 @@ spmm_rows_kernel(const SpmmParams p) {
   for (int tile0 = 0; tile0 < p.ncols; tile0 += G * CH) {
     Acc<VEC, CH, RED> acc;
     acc.init();
-    accumulate_range<VEC, CH, OP, RED, RMODE>(p, row_start, deg, nmax, lg, tile0, acc);
+    accumulate_range<VEC, CH, OP, RED, RMODE, T>(p, row_start, deg, nmax, lg, tile0, acc);
     if (active) {
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
@@ -200,12 +202,12 @@ spmm_rows_kernel(const SpmmParams p) {
             o.v[v] = p.row_scale ? __fdiv_rn(acc.a[c][v], scale) : acc.a[c][v];
           if constexpr (RED == DGLB_REDUCE_SUM) {
             if (p.accumulate) {
-              const FVec<VEC> prev = ldg_vec<VEC>(p.out + off);
+              const FVec<VEC> prev = ldg_vec_t<T, VEC>(reinterpret_cast<const T*>(p.out) + off);
 #pragma unroll
               for (int v = 0; v < VEC; ++v) o.v[v] = __fadd_rn(prev.v[v], o.v[v]);
             }
           }
-          st_vec<VEC>(p.out + off, o);
+          st_vec_t<T, VEC>(reinterpret_cast<T*>(p.out) + off, o);
           if constexpr (RED != DGLB_REDUCE_SUM) {
             if (p.arg_u) st_vec_i32<VEC>(p.arg_u + off, acc.au[c]);
             if (p.arg_e) st_vec_i32<VEC>(p.arg_e + off, acc.ae[c]);
@@ -217,7 +219,7 @@ spmm_rows_kernel(const SpmmParams p) {
 }
 
 // ------------------------------------------------------------------ hub rows: one CTA per segment
-template <int VEC, int CH, int OP, int RED, int RMODE>
+template <int VEC, int CH, int OP, int RED, int RMODE, typename T = float>
 __global__ void __launch_bounds__(kBlockThreads)
 spmm_hub_kernel(const SpmmParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -246,8 +248,8 @@ spmm_hub_kernel(const SpmmParams p) {
   for (int tile0 = 0; tile0 < p.ncols; tile0 += G * CH) {
     Acc<VEC, CH, RED> acc;
     acc.init();
-    accumulate_range<VEC, CH, OP, RED, RMODE>(p, (int64_t)row_start + seg_begin + my_begin, my_n, nmax, lg,
-                                              tile0, acc);
+    accumulate_range<VEC, CH, OP, RED, RMODE, T>(p, (int64_t)row_start + seg_begin + my_begin, my_n, nmax, lg,
+                                                 tile0, acc);
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int el = (c * G + lg) * VEC;
@@ -285,7 +287,7 @@ spmm_hub_kernel(const SpmmParams p) {
 }
 
 // fold the per-segment partial rows of every hub row, in segment (= CSR) order
-template <int RED>
+template <int RED, typename T = float>
 __global__ void __launch_bounds__(kBlockThreads) spmm_hub_combine_kernel(const SpmmParams p, int n_hub) {
   const int64_t idx = (int64_t)blockIdx.x * kBlockThreads + threadIdx.x;
   if (idx >= (int64_t)n_hub * p.D) return;
@@ -304,9 +306,9 @@ __global__ void __launch_bounds__(kBlockThreads) spmm_hub_combine_kernel(const S
   const int64_t off = row * (int64_t)p.D + kk;
   if (p.row_scale) a = __fdiv_rn(a, __ldg(p.row_scale + row));
   if constexpr (RED == DGLB_REDUCE_SUM) {
-    if (p.accumulate) a = __fadd_rn(p.out[off], a);
+    if (p.accumulate) a = __fadd_rn(load_scalar_t<T>(reinterpret_cast<const T*>(p.out) + off), a);
   }
-  p.out[off] = a;
+  store_scalar_t<T>(reinterpret_cast<T*>(p.out) + off, a);
   if constexpr (RED != DGLB_REDUCE_SUM) {
     if (p.arg_u) p.arg_u[off] = au;
     if (p.arg_e) p.arg_e[off] = ae;
@@ -380,26 +382,26 @@ __global__ void __launch_bounds__(kBlockThreads) spmm_generic_kernel(const Gener
 }
 
 // ------------------------------------------------------------------ dispatch
-template <int VEC, int CH, int OP, int RED, int RMODE>
+template <int VEC, int CH, int OP, int RED, int RMODE, typename T = float>
 static int launch_fast(const SpmmParams& p, int n_hub, int n_seg, cudaStream_t stream) {
   const int rows_per_block = kBlockThreads / p.G;
   const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
   if (blocks > 0) {
-    spmm_rows_kernel<VEC, CH, OP, RED, RMODE><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+    spmm_rows_kernel<VEC, CH, OP, RED, RMODE, T><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
     DGLB_LAUNCH_CHECK("spmm_rows_kernel");
   }
   if (n_hub > 0 && n_seg > 0) {
     const size_t smem = (size_t)kBlockThreads * CH * VEC * 4 * (RED == DGLB_REDUCE_SUM ? 1 : 3);
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
-      DGLB_CUDA(cudaFuncSetAttribute(spmm_hub_kernel<VEC, CH, OP, RED, RMODE>,
+      DGLB_CUDA(cudaFuncSetAttribute(spmm_hub_kernel<VEC, CH, OP, RED, RMODE, T>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set = true;
     }
-    spmm_hub_kernel<VEC, CH, OP, RED, RMODE><<<n_seg, kBlockThreads, smem, stream>>>(p);
+    spmm_hub_kernel<VEC, CH, OP, RED, RMODE, T><<<n_seg, kBlockThreads, smem, stream>>>(p);
     DGLB_LAUNCH_CHECK("spmm_hub_kernel");
     const int64_t cblocks = ((int64_t)n_hub * p.D + kBlockThreads - 1) / kBlockThreads;
-    spmm_hub_combine_kernel<RED><<<(unsigned)cblocks, kBlockThreads, 0, stream>>>(p, n_hub);
+    spmm_hub_combine_kernel<RED, T><<<(unsigned)cblocks, kBlockThreads, 0, stream>>>(p, n_hub);
     DGLB_LAUNCH_CHECK("spmm_hub_combine_kernel");
   }
   return DGLB_OK;
@@ -518,6 +520,53 @@ int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz
   spmm_generic_kernel<<<(unsigned)blocks, kBlockThreads, 0, stream>>>(g);
   DGLB_LAUNCH_CHECK("spmm_generic_kernel");
   return DGLB_OK;
+}
+
+// bf16 storage / fp32 accumulate: copy_lhs x sum (the SAGE aggregation and the micro-benchmark op)
+int spmm_csr_bf16(int op, int reduce, int64_t n_rows, const int32_t* indptr, const int32_t* indices,
+                  const void* X, int64_t D, void* out, const float* row_scale, int accumulate,
+                  const dglb_hub_t* hub, cudaStream_t stream) {
+  if (op != DGLB_OP_COPY_LHS || reduce != DGLB_REDUCE_SUM) {
+    set_error("gspmm: bf16 storage is implemented for copy_lhs with reducer sum (mean through row_scale)");
+    return DGLB_E_UNSUPPORTED;
+  }
+  if (n_rows == 0 || D == 0) return DGLB_OK;
+  if (D >= (1 << 30)) return DGLB_E_UNSUPPORTED;
+  SpmmParams p;
+  p.indptr = indptr; p.indices = indices; p.eids = nullptr;
+  p.X = static_cast<const float*>(X); p.W = nullptr; p.out = static_cast<float*>(out);
+  p.arg_u = nullptr; p.arg_e = nullptr; p.row_scale = row_scale;
+  p.n_rows = n_rows; p.D = (int)D; p.rhs_len = 0; p.inner = 1; p.accumulate = accumulate;
+  const bool use_hub = hub && hub->n_hub > 0 && hub->n_seg > 0 && hub->rows && hub->seg_ptr && hub->seg_hub &&
+                       hub->seg_len > 0;
+  const int n_hub = use_hub ? hub->n_hub : 0, n_seg = use_hub ? hub->n_seg : 0;
+  if (use_hub) {
+    const size_t need = (size_t)n_seg * (size_t)D * 4;
+    if (!hub->workspace || hub->workspace_bytes < need) { set_error("gspmm: hub workspace too small"); return DGLB_E_WORKSPACE; }
+    p.hub_rows = hub->rows; p.seg_ptr = hub->seg_ptr; p.seg_hub = hub->seg_hub; p.seg_len = hub->seg_len;
+    p.ws_val = static_cast<float*>(hub->workspace);
+  } else {
+    p.hub_rows = nullptr; p.seg_ptr = nullptr; p.seg_hub = nullptr; p.seg_len = 0; p.ws_val = nullptr;
+  }
+  p.ws_au = nullptr; p.ws_ae = nullptr;
+  p.hub_threshold = use_hub ? hub->threshold : INT32_MAX;
+  const int vec = min_int(pick_vec_bf16(D, X), pick_vec_bf16(D, out));
+  p.ncols = (int)(D / vec);
+  p.G = group_lanes(p.ncols);
+  p.log2G = 0;
+  while ((1 << p.log2G) < p.G) ++p.log2G;
+  const int per_lane = (p.ncols + p.G - 1) / p.G;
+  // 8 fp32 accumulators per chunk at VEC = 8: keep CH <= 2 there
+  const int ch = per_lane >= 4 ? (vec == 8 ? 2 : 4) : (per_lane >= 2 ? 2 : 1);
+#define DGLB_CASE(V, C) \
+  if (vec == V && ch == C) \
+    return launch_fast<V, C, DGLB_OP_COPY_LHS, DGLB_REDUCE_SUM, RMODE_NONE, __nv_bfloat16>(p, n_hub, n_seg, stream);
+  DGLB_CASE(8, 1) DGLB_CASE(8, 2)
+  DGLB_CASE(4, 1) DGLB_CASE(4, 2) DGLB_CASE(4, 4)
+  DGLB_CASE(2, 1) DGLB_CASE(2, 2) DGLB_CASE(2, 4)
+  DGLB_CASE(1, 1) DGLB_CASE(1, 2) DGLB_CASE(1, 4)
+#undef DGLB_CASE
+  return DGLB_E_UNSUPPORTED;
 }
 
 }  // namespace dglb

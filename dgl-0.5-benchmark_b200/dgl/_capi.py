@@ -16,6 +16,7 @@ OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "copy_lhs": 4, "copy_rhs": 5, "do
 REDUCERS = {"sum": 0, "max": 1, "min": 2}
 TARGETS = {"u": 0, "e": 1, "v": 2}
 F32 = 0
+BF16 = 1
 
 _lib = None
 _launches = 0  # number of C-ABI compute calls issued (bench.py reports kernel launches from this)

@@ -53,7 +53,7 @@ class GSpMM(torch.autograd.Function):
         X, Y, argX, argY, row_scale = ctx.saved_tensors
         dZ = dZ.contiguous()
         if row_scale is not None:  # fused mean: out = sum / deg  =>  d(sum) = dZ / deg
-            dZ = dZ / row_scale.view((-1,) + (1,) * (dZ.dim() - 1))
+            dZ = (dZ / row_scale.view((-1,) + (1,) * (dZ.dim() - 1))).to(dZ.dtype)
         dX = dY = None
         if op != "copy_rhs" and ctx.needs_input_grad[3]:
             g_rev = gidx.reverse()

@@ -79,6 +79,19 @@ def _check_float32(*ts):
             raise DGLError("dgl-b200 kernels compute in float32; got %s" % t.dtype)
 
 
+def _dtype_code(what, bf16_ok, *ts):
+    """C-ABI dtype of the operands: float32 everywhere; bfloat16 STORAGE (fp32 accumulate, one rounding
+    at the store) for gspmm copy_u sum/mean and gsddmm u_dot_v."""
+    dts = {t.dtype for t in ts if t is not None}
+    if dts == {torch.float32}:
+        return _capi.F32
+    if dts == {torch.bfloat16}:
+        if not bf16_ok:
+            raise DGLError("%s: bfloat16 storage is implemented for gspmm copy_u sum/mean and gsddmm u_dot_v only" % what)
+        return _capi.BF16
+    raise DGLError("%s: operands must be all float32 (or all bfloat16 where supported); got %s" % (what, sorted(map(str, dts))))
+
+
 def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None):
     """out[v] = reduce_{(s->v)} op(u[s], e[eid]).  Returns (out, (arg_u, arg_e)).
 
@@ -101,7 +114,7 @@ def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None):
         raise DGLError("gspmm: unknown reducer %s" % reduce_op)
     u = u if use_u else None
     e = e if use_e else None
-    _check_float32(u, e)
+    dtype = _dtype_code("gspmm", op == "copy_lhs" and reduce_op == "sum", u, e)
     dev = _capi.require_cuda(u, e, gidx.src)
     expand_u = expand_e = False
     if use_u:
@@ -143,7 +156,7 @@ def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None):
         hub, _keep, hub_launches = _hub_arg(csc.hubs(thr), dev, out_len, use_cmp)
         ndim, ls, rs = _shapes_for_abi(op, u, e)
         stream = _capi.enter(dev)
-        rc = l.dglb_gspmm_csr(_capi.OPS[op], _capi.REDUCERS[reduce_op], _capi.F32,
+        rc = l.dglb_gspmm_csr(_capi.OPS[op], _capi.REDUCERS[reduce_op], dtype,
                               csc.n_rows, csc.n_cols, csc.nnz,
                               _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(csc.eids),
                               _capi.ptr(u), _capi.ptr(e), ndim, ls, rs,
@@ -180,7 +193,8 @@ def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
                        "type.".format(lhs.dtype, rhs.dtype))
     lhs = lhs if use_lhs else None
     rhs = rhs if use_rhs else None
-    _check_float32(lhs, rhs)
+    dtype = _dtype_code("gsddmm", op == "dot" and lhs_target == "u" and rhs_target == "v" and "csc" in gidx.formats(),
+                        lhs, rhs)
     dev = _capi.require_cuda(lhs, rhs, gidx.src)
     n_of = {"u": gidx.n_src, "e": gidx.n_edges, "v": gidx.n_dst}
     expand_lhs = expand_rhs = False
@@ -213,7 +227,7 @@ def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
                 width *= s
             thr = _hub_threshold(width)
             hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
-            rc = l.dglb_gsddmm_csr(_capi.OPS[op], _capi.F32, lt, rt, csc.n_rows, csc.n_cols, csc.nnz,
+            rc = l.dglb_gsddmm_csr(_capi.OPS[op], dtype, lt, rt, csc.n_rows, csc.n_cols, csc.nnz,
                                    _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(csc.eids),
                                    _capi.ptr(lhs), _capi.ptr(rhs), ndim, ls, rs, _capi.ptr(out),
                                    hub, stream)

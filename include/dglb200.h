@@ -69,7 +69,8 @@ extern "C" {
 
 /* element types */
 #define DGLB_F32 0
-#define DGLB_BF16 1 /* storage bf16, fp32 accumulate (reserved; not all kernels) */
+#define DGLB_BF16 1 /* bf16 storage, fp32 accumulate, one rounding at the store: gspmm copy_lhs x sum
+                       (+ row_scale) and gsddmm_csr u_dot_v; other entry points return DGLB_E_UNSUPPORTED */
 
 #define DGLB_MAX_BCAST_NDIM 5
 
