@@ -133,6 +133,16 @@ def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None):
     ref = u if use_u else e
     out_shape = (gidx.n_dst,) + tuple(feat_shape)
     use_cmp = reduce_op in ("max", "min")
+    if dtype == _capi.BF16 and out is None:
+        # bf16 rows whose width is not a multiple of 8 (e.g. 602) would be gathered with 4-byte loads:
+        # zero-pad the row once (one cheap pass), run with 128-bit loads, slice the padding off
+        width = 1
+        for s_ in feat_shape:
+            width *= s_
+        if width >= 32 and width % 8:
+            padded = torch.nn.functional.pad(u.reshape(u.shape[0], width), (0, 8 - width % 8))
+            res, _ = _gspmm(gidx, op, reduce_op, padded, None, row_scale)
+            return res[:, :width].reshape(out_shape), (None, None)
     arg_u = arg_e = None
     if out is not None:
         if reduce_op != "sum" or tuple(out.shape) != out_shape or not out.is_contiguous() or out.dtype != ref.dtype:
@@ -212,6 +222,10 @@ def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
         rhs = rhs.contiguous()
     feat_shape = infer_broadcast_shape(op, lhs.shape[1:] if use_lhs else (1,), rhs.shape[1:] if use_rhs else (1,))
     ref = lhs if use_lhs else rhs
+    if dtype == _capi.BF16 and lhs.dim() == 2 and lhs.shape[1] >= 32 and lhs.shape[1] % 8:
+        pad = 8 - lhs.shape[1] % 8  # zero columns do not change the dot product; 128-bit loads instead of 32-bit
+        return _gsddmm(gidx, op, torch.nn.functional.pad(lhs, (0, pad)), torch.nn.functional.pad(rhs, (0, pad)),
+                       lhs_target, rhs_target)
     out = torch.empty((gidx.n_edges,) + tuple(feat_shape), dtype=ref.dtype, device=dev)
     if gidx.n_edges > 0 and out.numel() > 0:
         l = _capi.lib()
