@@ -133,6 +133,41 @@ __device__ __forceinline__ void st_vec_t(T* p, const FVec<VEC>& r) {
   }
 }
 
+// Raw staging registers: gathered rows stay PACKED until they are consumed (bf16: VEC/2 registers
+// instead of VEC converted floats -- at VEC = 8 that halves the staging footprint of a load batch).
+template <typename T, int VEC>
+struct RawVec {
+  static constexpr int NW = sizeof(T) == 4 ? VEC : (VEC + 1) / 2;
+  uint32_t w[NW];
+  template <int I>
+  __device__ __forceinline__ float get() const {
+    if constexpr (sizeof(T) == 4) return __uint_as_float(w[I]);
+    else return (I & 1) ? bf16hi(w[I / 2]) : bf16lo(w[I / 2]);
+  }
+  __device__ __forceinline__ float at(int i) const {  // i is a compile-time constant after unrolling
+    if constexpr (sizeof(T) == 4) return __uint_as_float(w[i]);
+    else return (i & 1) ? bf16hi(w[i >> 1]) : bf16lo(w[i >> 1]);
+  }
+};
+
+template <typename T, int VEC>
+__device__ __forceinline__ RawVec<T, VEC> ldg_raw(const T* p) {
+  RawVec<T, VEC> r;
+  constexpr int BYTES = (int)sizeof(T) * VEC;
+  if constexpr (BYTES == 16) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    r.w[0] = t.x; r.w[1] = t.y; r.w[2] = t.z; r.w[3] = t.w;
+  } else if constexpr (BYTES == 8) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    r.w[0] = t.x; r.w[1] = t.y;
+  } else if constexpr (BYTES == 4) {
+    r.w[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+  } else {
+    r.w[0] = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p));
+  }
+  return r;
+}
+
 template <typename T>
 __device__ __forceinline__ float load_scalar_t(const T* p) {
   if constexpr (sizeof(T) == 4) return *reinterpret_cast<const float*>(p);

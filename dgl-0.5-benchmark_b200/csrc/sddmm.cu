@@ -124,12 +124,12 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmPar
   const T* __restrict__ vrow = reinterpret_cast<const T*>(p.V) + row * (int64_t)p.D;
   const T* __restrict__ ubase = reinterpret_cast<const T*>(p.U);
   T* __restrict__ obase = reinterpret_cast<T*>(p.out);
-  FVec<VEC> vreg[CH];
+  RawVec<T, VEC> vreg[CH];
   if constexpr (SINGLE) {
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int vc = c * G + lg;
-      if (n > 0 && vc < p.ncols) vreg[c] = ldg_vec_t<T, VEC>(vrow + vc * VEC);
+      if (n > 0 && vc < p.ncols) vreg[c] = ldg_raw<T, VEC>(vrow + vc * VEC);
     }
   }
   for (int off = 0; off < nmax; off += G) {
@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmPar
         part[u] = 0.f;
       }
       for (int tile0 = 0; tile0 < (SINGLE ? 1 : p.ncols); tile0 += tile_cols) {
-        FVec<VEC> xv[U][CH];
-        FVec<VEC> vv[CH];
+        RawVec<T, VEC> xv[U][CH];
+        RawVec<T, VEC> vv[CH];
         bool colv[CH];
         // phase 1: issue every load of this (edge batch, tile) before the first use
 #pragma unroll
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmPar
           const int vc = tile0 + c * G + lg;
           colv[c] = vc < p.ncols;
           if constexpr (!SINGLE) {
-            if (colv[c] && m > 0) vv[c] = ldg_vec_t<T, VEC>(vrow + vc * VEC);
+            if (colv[c] && m > 0) vv[c] = ldg_raw<T, VEC>(vrow + vc * VEC);
           }
         }
 #pragma unroll
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmPar
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             if ((t + u) < m && colv[c])
-              xv[u][c] = ldg_vec_t<T, VEC>(ubase + (int64_t)cc[u] * p.D + (tile0 + c * G + lg) * VEC);
+              xv[u][c] = ldg_raw<T, VEC>(ubase + (int64_t)cc[u] * p.D + (tile0 + c * G + lg) * VEC);
           }
         }
         // phase 2: multiply-accumulate
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmPar
             if ((t + u) < m && colv[c]) {
 #pragma unroll
               for (int v = 0; v < VEC; ++v)
-                part[u] = fmaf(xv[u][c].v[v], SINGLE ? vreg[c].v[v] : vv[c].v[v], part[u]);
+                part[u] = fmaf(xv[u][c].at(v), SINGLE ? vreg[c].at(v) : vv[c].at(v), part[u]);
             }
           }
         }
@@ -379,11 +379,7 @@ static int dispatch_dot(const SddmmParams& p, int ch, int n_hub, cudaStream_t st
   }
   if (ch == 2)
     return single ? launch_dot<VEC, 2, 5, true, T>(p, n_hub, stream) : launch_dot<VEC, 2, 5, false, T>(p, n_hub, stream);
-  if constexpr (VEC < 8) {
-    return single ? launch_dot<VEC, 4, 5, true, T>(p, n_hub, stream) : launch_dot<VEC, 4, 5, false, T>(p, n_hub, stream);
-  } else {
-    return DGLB_E_UNSUPPORTED;  // VEC = 8 keeps CH <= 2 (register budget)
-  }
+  return single ? launch_dot<VEC, 4, 5, true, T>(p, n_hub, stream) : launch_dot<VEC, 4, 5, false, T>(p, n_hub, stream);
 }
 
 template <int VEC, int CH, int OP>
@@ -460,7 +456,8 @@ int sddmm_csr_fast_f32(int op, int64_t n_dst, const int32_t* indptr, const int32
   while ((1 << p.log2G) < p.G) ++p.log2G;
   if (op == DGLB_OP_DOT && p.H == 1) p.seg = p.G;
   const int per_lane = (p.ncols + p.G - 1) / p.G;
-  const int ch = per_lane >= 4 ? (vec == 8 ? 2 : 4) : (per_lane >= 2 ? 2 : 1);
+  const int ch = (op == DGLB_OP_DOT && dtype == DGLB_BF16) ? (per_lane >= 3 ? 4 : (per_lane >= 2 ? 2 : 1))
+                                                           : (per_lane >= 4 ? 4 : (per_lane >= 2 ? 2 : 1));
   if (op == DGLB_OP_DOT) {
     if (p.H > 1 && ch != 1) return DGLB_E_UNSUPPORTED;
     if (dtype == DGLB_BF16) {

@@ -120,7 +120,7 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0
     const int mmax = min(G, nmax - off);
     for (int t = 0; t < mmax; t += U) {
       int cc[U], ee[U];
-      FVec<VEC> xv[U][CH];
+      RawVec<T, VEC> xv[U][CH];  // packed until consumed
       FVec<(VEC > 4 ? 4 : VEC)> wv[U][CH];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -134,7 +134,7 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0
         for (int c = 0; c < CH; ++c) {
           if (valid && colv[c]) {
             if constexpr (USE_L)
-              xv[u][c] = ldg_vec_t<T, VEC>(reinterpret_cast<const T*>(p.X) + (int64_t)cc[u] * p.D + k[c]);
+              xv[u][c] = ldg_raw<T, VEC>(reinterpret_cast<const T*>(p.X) + (int64_t)cc[u] * p.D + k[c]);
             if constexpr (RMODE == RMODE_FULL)
               wv[u][c] = ldg_vec_t<float, (VEC > 4 ? 4 : VEC)>(p.W + (int64_t)ee[u] * p.D + k[c]);
             if constexpr (RMODE == RMODE_HEAD)
@@ -152,10 +152,10 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0
             for (int v = 0; v < VEC; ++v) {
               float val;
               const float w = (RMODE == RMODE_HEAD) ? wv[u][c].v[0] : (USE_R ? wv[u][c].v[v] : 0.f);
-              if constexpr (OP == DGLB_OP_COPY_LHS) val = xv[u][c].v[v];
+              if constexpr (OP == DGLB_OP_COPY_LHS) val = xv[u][c].at(v);
               else if constexpr (OP == DGLB_OP_COPY_RHS) val = w;
-              else if constexpr (OP == DGLB_OP_MUL) val = __fmul_rn(xv[u][c].v[v], w);
-              else val = __fadd_rn(xv[u][c].v[v], w);
+              else if constexpr (OP == DGLB_OP_MUL) val = __fmul_rn(xv[u][c].at(v), w);
+              else val = __fadd_rn(xv[u][c].at(v), w);
               if constexpr (RED == DGLB_REDUCE_SUM) {
                 acc.a[c][v] = __fadd_rn(acc.a[c][v], val);
               } else {
@@ -556,12 +556,11 @@ int spmm_csr_bf16(int op, int reduce, int64_t n_rows, const int32_t* indptr, con
   p.log2G = 0;
   while ((1 << p.log2G) < p.G) ++p.log2G;
   const int per_lane = (p.ncols + p.G - 1) / p.G;
-  // 8 fp32 accumulators per chunk at VEC = 8: keep CH <= 2 there
-  const int ch = per_lane >= 4 ? (vec == 8 ? 2 : 4) : (per_lane >= 2 ? 2 : 1);
+  const int ch = per_lane >= 3 ? 4 : (per_lane >= 2 ? 2 : 1);
 #define DGLB_CASE(V, C) \
   if (vec == V && ch == C) \
     return launch_fast<V, C, DGLB_OP_COPY_LHS, DGLB_REDUCE_SUM, RMODE_NONE, __nv_bfloat16>(p, n_hub, n_seg, stream);
-  DGLB_CASE(8, 1) DGLB_CASE(8, 2)
+  DGLB_CASE(8, 1) DGLB_CASE(8, 2) DGLB_CASE(8, 4)
   DGLB_CASE(4, 1) DGLB_CASE(4, 2) DGLB_CASE(4, 4)
   DGLB_CASE(2, 1) DGLB_CASE(2, 2) DGLB_CASE(2, 4)
   DGLB_CASE(1, 1) DGLB_CASE(1, 2) DGLB_CASE(1, 4)
