@@ -36,12 +36,14 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
+
 constexpr int kBlockThreads = 256;
 
 // ------------------------------------------------------------------ small vectors of floats
 template <int VEC>
 struct FVec {
   float v[VEC];
+  __device__ __forceinline__ float at(int i) const { return v[i]; }
 };
 
 // read-only (non-coherent) vector load of VEC consecutive floats; p must be VEC*4-byte aligned
@@ -166,6 +168,22 @@ __device__ __forceinline__ RawVec<T, VEC> ldg_raw(const T* p) {
     r.w[0] = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p));
   }
   return r;
+}
+
+// Staging type of a gathered chunk: fp32 rows keep the plain float vector (this is the code shape the
+// fp32 kernels were tuned with -- the packed form made ptxas interleave loads and FMAs in the narrow
+// SDDMM variants, 1.5x slower); bf16 rows stay packed.
+template <typename T, int VEC>
+struct StageSel { using type = RawVec<T, VEC>; };
+template <int VEC>
+struct StageSel<float, VEC> { using type = FVec<VEC>; };
+template <typename T, int VEC>
+using StageVec = typename StageSel<T, VEC>::type;
+
+template <typename T, int VEC>
+__device__ __forceinline__ StageVec<T, VEC> ldg_stage(const T* p) {
+  if constexpr (sizeof(T) == 4) return ldg_vec<VEC>(reinterpret_cast<const float*>(p));
+  else return ldg_raw<T, VEC>(p);
 }
 
 template <typename T>

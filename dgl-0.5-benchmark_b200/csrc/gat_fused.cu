@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatPara
             }
           }
         }
-#pragma unroll
+  #pragma unroll
         for (int u = 0; u < U; ++u) {
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_bwd_kernel(const GatPara
             }
           }
         }
-#pragma unroll
+  #pragma unroll
         for (int u = 0; u < U; ++u) {
 #pragma unroll
           for (int c = 0; c < CH; ++c) {

@@ -124,12 +124,12 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmPar
   const T* __restrict__ vrow = reinterpret_cast<const T*>(p.V) + row * (int64_t)p.D;
   const T* __restrict__ ubase = reinterpret_cast<const T*>(p.U);
   T* __restrict__ obase = reinterpret_cast<T*>(p.out);
-  RawVec<T, VEC> vreg[CH];
+  StageVec<T, VEC> vreg[CH];
   if constexpr (SINGLE) {
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int vc = c * G + lg;
-      if (n > 0 && vc < p.ncols) vreg[c] = ldg_raw<T, VEC>(vrow + vc * VEC);
+      if (n > 0 && vc < p.ncols) vreg[c] = ldg_stage<T, VEC>(vrow + vc * VEC);
     }
   }
   for (int off = 0; off < nmax; off += G) {
@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmPar
         part[u] = 0.f;
       }
       for (int tile0 = 0; tile0 < (SINGLE ? 1 : p.ncols); tile0 += tile_cols) {
-        RawVec<T, VEC> xv[U][CH];
-        RawVec<T, VEC> vv[CH];
+        StageVec<T, VEC> xv[U][CH];
+        StageVec<T, VEC> vv[CH];
         bool colv[CH];
         // phase 1: issue every load of this (edge batch, tile) before the first use
 #pragma unroll
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmPar
           const int vc = tile0 + c * G + lg;
           colv[c] = vc < p.ncols;
           if constexpr (!SINGLE) {
-            if (colv[c] && m > 0) vv[c] = ldg_raw<T, VEC>(vrow + vc * VEC);
+            if (colv[c] && m > 0) vv[c] = ldg_stage<T, VEC>(vrow + vc * VEC);
           }
         }
 #pragma unroll
@@ -167,10 +167,10 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_dot_kernel(const SddmmPar
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             if ((t + u) < m && colv[c])
-              xv[u][c] = ldg_raw<T, VEC>(ubase + (int64_t)cc[u] * p.D + (tile0 + c * G + lg) * VEC);
+              xv[u][c] = ldg_stage<T, VEC>(ubase + (int64_t)cc[u] * p.D + (tile0 + c * G + lg) * VEC);
           }
         }
-        // phase 2: multiply-accumulate
+          // phase 2: multiply-accumulate
 #pragma unroll
         for (int u = 0; u < U; ++u) {
 #pragma unroll
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kBlockThreads) sddmm_ew_kernel(const SddmmPara
                 xv[u][c] = ldg_vec<VEC>(p.U + (int64_t)cc[u] * p.D + (tile0 + c * G + lg) * VEC);
           }
         }
-#pragma unroll
+  #pragma unroll
         for (int u = 0; u < U; ++u) {
           const bool valid = (t + u) < m;
 #pragma unroll

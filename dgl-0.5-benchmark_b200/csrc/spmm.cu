@@ -120,7 +120,7 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0
     const int mmax = min(G, nmax - off);
     for (int t = 0; t < mmax; t += U) {
       int cc[U], ee[U];
-      RawVec<T, VEC> xv[U][CH];  // packed until consumed
+      StageVec<T, VEC> xv[U][CH];  // bf16 rows stay packed until consumed
       FVec<(VEC > 4 ? 4 : VEC)> wv[U][CH];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -134,7 +134,7 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0
         for (int c = 0; c < CH; ++c) {
           if (valid && colv[c]) {
             if constexpr (USE_L)
-              xv[u][c] = ldg_raw<T, VEC>(reinterpret_cast<const T*>(p.X) + (int64_t)cc[u] * p.D + k[c]);
+              xv[u][c] = ldg_stage<T, VEC>(reinterpret_cast<const T*>(p.X) + (int64_t)cc[u] * p.D + k[c]);
             if constexpr (RMODE == RMODE_FULL)
               wv[u][c] = ldg_vec_t<float, (VEC > 4 ? 4 : VEC)>(p.W + (int64_t)ee[u] * p.D + k[c]);
             if constexpr (RMODE == RMODE_HEAD)
