@@ -1,0 +1,56 @@
+"""Regression guard (CPU-only, cuobjdump): the hot gather kernels must issue a whole batch of
+neighbour-row loads before the first floating-point consumer.  Twice in round 1 a harmless-looking
+source change made the compiler interleave each load with its FMA (1-3 loads in flight instead of 8),
+costing 1.5-2.6x at identical DRAM traffic (profiles/r01_notes.md); this test catches that in SASS."""
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+KERNELS = {  # mangled-name fragment -> minimum run of vector loads with no FP instruction in between
+    "spmm_rows_kernelILi2ELi4ELi4ELi0ELi0EfEE": 6,        # gspmm copy_u_sum, D=602 (LDG.64)
+    "spmm_rows_kernelILi4ELi1ELi4ELi0ELi0EfEE": 6,        # gspmm copy_u_sum, D=64..128 (LDG.128)
+    "spmm_rows_kernelILi4ELi2ELi4ELi0ELi0EfEE": 6,        # D=256
+    "sddmm_dot_kernelILi2ELi4ELi5ELb0ELb0EfEE": 8,        # gsddmm u_dot_v, D=602
+    "sddmm_dot_kernelILi4ELi1ELi4ELb1ELb0EfEE": 6,        # D=64
+    "sddmm_dot_kernelILi4ELi2ELi5ELb1ELb0EfEE": 6,        # D=256
+    "spmm_rows_kernelILi8ELi4ELi4ELi0ELi0E13__nv_bfloat16": 6,  # bf16 storage, D=608
+}
+
+
+@pytest.fixture(scope="module")
+def sass():
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("dglb_build", os.path.join(ROOT, "dgl-0.5-benchmark_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = mod.build()
+    out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    funcs, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            funcs[name] = []
+        elif name is not None:
+            funcs[name].append(line)
+    return funcs
+
+
+@pytest.mark.parametrize("fragment,min_run", sorted(KERNELS.items()))
+def test_gathers_are_issued_as_a_batch(sass, fragment, min_run):
+    names = [n for n in sass if fragment in n]
+    assert names, "kernel %s not found in libdglb200.so" % fragment
+    best = run = 0
+    for line in sass[names[0]]:
+        if re.search(r"\bLDG\.E\.(64|128)", line):
+            run += 1
+            best = max(best, run)
+        elif re.search(r"\b(FFMA|FADD|FMUL)\b", line):
+            run = 0
+    assert best >= min_run, "%s: longest run of vector gathers before an FP consumer is %d (< %d)" % (fragment, best, min_run)
