@@ -117,11 +117,16 @@ size_t dglb_hub_workspace_bytes(int64_t n_seg, int64_t out_len, int with_args) {
 }
 
 int32_t dglb_default_hub_threshold(int64_t out_len) {
-  // bound the bytes one row-group streams (~1.5 MB) so a hub cannot become the kernel's tail
+  // A row-task is a chain of dependent batches (G edges per round trip), so its duration is set by its
+  // EDGE count, not its bytes: measured on a power-law reddit graph the best cut-off is ~160-400 edges
+  // from D=64 to D=602 (profiles/r01_notes.md).  Narrow rows (few lanes per row) get a lower cut-off.
   if (out_len < 1) out_len = 1;
-  int64_t t = (int64_t)(1536 * 1024) / (out_len * 4);
-  if (t < 256) t = 256;
-  if (t > 8192) t = 8192;
+  const int64_t ncols = (out_len + 3) / 4;
+  int64_t g = 1;
+  while (g < 32 && g < ncols) g <<= 1;
+  int64_t t = 16 * g;
+  if (t < 64) t = 64;
+  if (t > 256) t = 256;
   return (int32_t)t;
 }
 

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--widths", default="64,100")
     ap.add_argument("--degree", default="uniform")
     ap.add_argument("--order", default="shuffled")
+    ap.add_argument("--hub-bytes", type=int, default=0, help="override: hub threshold = hub_bytes / (4*D)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     n, e, _, _ = synthetic.SHAPES[args.shape]
@@ -43,10 +44,13 @@ def main():
     g = dgl.graph((torch.from_numpy(src), torch.from_numpy(dst)), num_nodes=n).int().to(dev)
     peak, _ = measured_peak()
     p = 0 if args.order == "dst_sorted" else 1
+    from dgl import sparse as K
     for D in [int(x) for x in args.widths.split(",")]:
+        K.HUB_THRESHOLD = max(32, args.hub_bytes // (4 * D)) if args.hub_bytes else None
         X, V = torch.rand(n, D, device=dev), torch.rand(n, D, device=dev)
         W = torch.rand(e, 1, device=dev)
-        res = {"shape": args.shape, "nodes": n, "edges": e, "D": D, "degree": args.degree, "order": args.order}
+        res = {"shape": args.shape, "nodes": n, "edges": e, "D": D, "degree": args.degree, "order": args.order,
+               "hub_threshold": K.HUB_THRESHOLD}
         for name, fn, B in (
                 ("copy_u_sum", lambda: dgl.ops.gspmm(g, "copy_lhs", "sum", X, None), spmm_bytes(n, e, D)),
                 ("copy_u_mean", lambda: dgl.ops.gspmm(g, "copy_lhs", "mean", X, None), spmm_bytes(n, e, D)),

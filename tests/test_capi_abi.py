@@ -64,5 +64,5 @@ def test_argument_errors_are_reported_without_a_gpu(built_lib):
     rc = l.dglb_gsddmm_coo(0, 0, 0, 2, 1, 1, 1, None, None, ctypes.c_void_p(8), ctypes.c_void_p(8), 1, shp, bad,
                            ctypes.c_void_p(8), None)
     assert rc == -1 and b"broadcast" in l.dglb_last_error()
-    assert l.dglb_default_hub_threshold(602) == 653
-    assert l.dglb_default_hub_threshold(1) == 8192
+    assert l.dglb_default_hub_threshold(602) == 256
+    assert l.dglb_default_hub_threshold(16) == 64
