@@ -116,6 +116,14 @@ size_t dglb_hub_workspace_bytes(int64_t n_seg, int64_t out_len, int with_args) {
   return (size_t)n_seg * (size_t)out_len * 4 * (with_args ? 3 : 1);
 }
 
+int32_t dglb_default_row_hub_threshold(int64_t out_len) {
+  if (out_len < 1) out_len = 1;
+  int64_t t = (int64_t)(1536 * 1024) / (out_len * 4);
+  if (t < 256) t = 256;
+  if (t > 8192) t = 8192;
+  return (int32_t)t;
+}
+
 int32_t dglb_default_hub_threshold(int64_t out_len) {
   // A row-task is a chain of dependent batches (G edges per round trip), so its duration is set by its
   // EDGE count, not its bytes: measured on a power-law reddit graph the best cut-off is ~160-400 edges

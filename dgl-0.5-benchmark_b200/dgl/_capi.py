@@ -51,6 +51,7 @@ _SIGNATURES = {
     "dglb_is_identity_perm": (_int, [_i64, _vp, _vp, _vp]),
     "dglb_csr_find_hub_rows": (_int, [_i64, _vp, _i32, _vp, _i64, _vp, _vp]),
     "dglb_default_hub_threshold": (_i32, [_i64]),
+    "dglb_default_row_hub_threshold": (_i32, [_i64]),
     "dglb_hub_workspace_bytes": (ctypes.c_size_t, [_i64, _i64, _int]),
     "dglb_gspmm_csr": (_int, [_int, _int, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _shape_t,
                               _shape_t, _vp, _vp, _vp, _vp, _int, _hub_t, _vp]),

@@ -20,9 +20,13 @@ _TARGET = _capi.TARGETS
 HUB_THRESHOLD = None
 
 
-def _hub_threshold(width):
+def _hub_threshold(width, row_cta=False):
+    """Hub cut-off for a feature width: segmented path (gspmm / gsddmm) or, with row_cta=True, the
+    one-CTA-per-row path of edge_softmax and the fused GAT kernels."""
     if HUB_THRESHOLD is not None:
         return int(HUB_THRESHOLD)
+    if row_cta:
+        return _capi.lib().dglb_default_row_hub_threshold(int(width))
     return _capi.lib().dglb_default_hub_threshold(int(width))
 
 
@@ -272,7 +276,7 @@ def _edge_softmax_fwd(gidx, logits):
     heads = logits.numel() // gidx.n_edges
     csc = gidx.csc()
     l = _capi.lib()
-    thr = _hub_threshold(max(heads, 64))
+    thr = _hub_threshold(max(heads, 64), row_cta=True)
     hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
     stream = _capi.enter(dev)
     rc = l.dglb_edge_softmax_fwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(csc.eids),
@@ -293,7 +297,7 @@ def _edge_softmax_bwd(gidx, out, grad_out):
     heads = out.numel() // gidx.n_edges
     csc = gidx.csc()
     l = _capi.lib()
-    thr = _hub_threshold(max(heads, 64))
+    thr = _hub_threshold(max(heads, 64), row_cta=True)
     hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
     stream = _capi.enter(dev)
     rc = l.dglb_edge_softmax_bwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(csc.eids),
@@ -320,7 +324,7 @@ def _gat_fwd(gidx, ft, el, er, slope, dropout_p, seed, want_scores=False, eids=N
         return rst, row_max, row_sum, scores
     csc = gidx.csc()
     l = _capi.lib()
-    thr = _hub_threshold(H * F)
+    thr = _hub_threshold(H * F, row_cta=True)
     hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
     stream = _capi.enter(dev)
     rc = l.dglb_gat_fused_fwd(_capi.F32, csc.n_rows, csc.n_cols, csc.nnz, H, F, float(slope), float(dropout_p),
@@ -342,7 +346,7 @@ def _gat_bwd_dst(gidx, ft, el, er, row_max, row_sum, grad_rst, slope, dropout_p,
     grad_er = torch.empty((gidx.n_dst, H), dtype=ft.dtype, device=dev)
     if gidx.n_dst:
         csc = gidx.csc()
-        thr = _hub_threshold(H * F)
+        thr = _hub_threshold(H * F, row_cta=True)
         hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
         stream = _capi.enter(dev)
         rc = _capi.lib().dglb_gat_fused_bwd_dst(
@@ -365,7 +369,7 @@ def _gat_bwd_src(csr, ft, el, row_pack, grad_rst, slope, dropout_p, seed, eids=N
     grad_ft = torch.empty_like(ft)
     grad_el = torch.empty((csr.n_rows, H), dtype=ft.dtype, device=dev)
     if csr.n_rows:
-        thr = _hub_threshold(H * F)
+        thr = _hub_threshold(H * F, row_cta=True)
         hub, _keep, hub_launches = _hub_arg(csr.hubs(thr))
         stream = _capi.enter(dev)
         rc = _capi.lib().dglb_gat_fused_bwd_src(

@@ -108,8 +108,12 @@ int dglb_is_identity_perm(int64_t n, const int32_t* data, int32_t* flag, void* s
  * hub_rows (capacity `cap`) the ids (writes beyond cap are dropped, the count stays exact). */
 int dglb_csr_find_hub_rows(int64_t n_rows, const int32_t* indptr, int32_t threshold,
                            int32_t* hub_rows, int64_t cap, int32_t* n_hub, void* stream);
-/* threshold the library recommends for a given feature width (elements) */
+/* thresholds the library recommends for a given feature width (elements): the first for the
+ * segmented hub path of gspmm / gsddmm (64-256 edges: a row-task's duration follows its edge count),
+ * the second for the one-CTA-per-hub-row path of edge_softmax and the fused GAT kernels (only real
+ * hubs: ~1.5 MB of gather per row-task, 256-8192 edges) */
 int32_t dglb_default_hub_threshold(int64_t out_len);
+int32_t dglb_default_row_hub_threshold(int64_t out_len);
 
 /* Hub-row metadata handed to the compute entry points (NULL = treat every row as an ordinary row).
  * Rows with nnz > threshold are skipped by the row-per-group kernels.  gspmm / gsddmm cut each hub
