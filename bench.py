@@ -295,26 +295,39 @@ def main():
             for D in sorted(WIDTHS, reverse=True):  # widest first: its copies hide behind the rest of the sweep
                 with torch.cuda.stream(s_in):
                     X = host[D][0].to(dev, non_blocking=True)
+                    ex = torch.cuda.Event()
+                    ex.record(s_in)
                     V = host[D][1].to(dev, non_blocking=True)
-                    e = torch.cuda.Event()
-                    e.record(s_in)
-                staged.append((D, X, V, e))
+                    ev_ = torch.cuda.Event()
+                    ev_.record(s_in)
+                staged.append((D, X, V, ex, ev_))
             done = []
-            for D, X, V, e in staged:
-                s_main.wait_event(e)
+            for D, X, V, ex, ev_ in staged:
+                s_main.wait_event(ex)            # gspmm needs X only: start as soon as it has landed
                 X.record_stream(s_main)
                 V.record_stream(s_main)
                 if part is None:
                     out = dgl.ops.gspmm(g, "copy_lhs", "sum", X, None)
+                    c1 = torch.cuda.Event()
+                    c1.record(s_main)
+                    s_out.wait_event(c1)
+                    with torch.cuda.stream(s_out):
+                        host_out[D][0].copy_(out, non_blocking=True)
+                    s_main.wait_event(ev_)
                     sc = dgl.ops.gsddmm(g, "dot", X, V)
                 else:
                     out, buf = part.pipelined_copy_u_sum(X)
+                    c1 = torch.cuda.Event()
+                    c1.record(s_main)
+                    s_out.wait_event(c1)
+                    with torch.cuda.stream(s_out):
+                        host_out[D][0].copy_(out, non_blocking=True)
+                    s_main.wait_event(ev_)
                     sc = torch.cat(part.pipelined_u_dot_v(None, V, gathered=(buf, [None] * part.chunks)), 0)
                 c = torch.cuda.Event()
                 c.record(s_main)
                 s_out.wait_event(c)
                 with torch.cuda.stream(s_out):
-                    host_out[D][0].copy_(out, non_blocking=True)
                     host_out[D][1].copy_(sc, non_blocking=True)
                 out.record_stream(s_out)
                 sc.record_stream(s_out)
