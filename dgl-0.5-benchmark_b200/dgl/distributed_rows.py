@@ -175,11 +175,17 @@ class RowPartition:
         """Row-partitioned gsddmm(dot) for the edges whose destination is local."""
         return ops.gsddmm(self.local_graph, "dot", self.all_gather_rows(u_local), v_local)
 
+    MIN_PIPELINE_CHUNK_BYTES = 12 << 20   # per-rank bytes of one gather chunk below which pipelining is skipped
+
+    def _chunk_bytes(self, buf):
+        return buf.numel() * buf.element_size() // (self.chunks * self.world)
+
     def pipelined_copy_u_sum(self, x_local, gathered=None):
         """gspmm(copy_lhs, sum) over the rank's rows, one source chunk at a time behind its gather
         (no autograd).  Returns (out, gather buffer).  `gathered` = (buffer, works) already in flight."""
         buf, works = gathered if gathered is not None else self.all_gather_rows(x_local, async_op=True)
-        if self.chunk_blocks is None:
+        if self.chunk_blocks is None or self._chunk_bytes(buf) < self.MIN_PIPELINE_CHUNK_BYTES:
+            # small operand: K tiny launches would cost more than the overlap buys -- one kernel
             for w in works:
                 if w is not None:
                     w.wait()
@@ -199,7 +205,7 @@ class RowPartition:
         """gsddmm(dot) for the rank's edges per source chunk; returns the list of per-chunk (E_k, 1)
         results.  `gathered` = (buffer, works) of the u operand (works may already be complete)."""
         buf, works = gathered if gathered is not None else self.all_gather_rows(u_local, async_op=True)
-        if self.chunk_blocks is None:
+        if self.chunk_blocks is None or self._chunk_bytes(buf) < self.MIN_PIPELINE_CHUNK_BYTES:
             for w in works:
                 if w is not None:
                     w.wait()
