@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--widths", default="64,100")
     ap.add_argument("--degree", default="uniform")
     ap.add_argument("--order", default="shuffled")
+    ap.add_argument("--softmax-heads", default="", help="comma list: also time edge_softmax fwd/bwd with H heads")
     ap.add_argument("--hub-bytes", type=int, default=0, help="override: hub threshold = hub_bytes / (4*D)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -60,6 +61,20 @@ def main():
             ms = timeit(fn)
             res[name] = {"ms": round(ms, 4), "gbs": round(B / ms / 1e6), "frac": round(B / ms / 1e6 / peak, 3)}
         print(json.dumps(res), flush=True)
+    if args.softmax_heads:
+        from dgl import sparse as K2
+        for H in [int(x) for x in args.softmax_heads.split(",")]:
+            z = torch.randn(e, H, device=dev)
+            a = K2._edge_softmax_fwd(g._graph, z)
+            gr = torch.randn(e, H, device=dev)
+            Bf = 4 * (n + 1) + 4 * p * e + 2 * 4 * H * e
+            Bb = 4 * (n + 1) + 4 * p * e + 3 * 4 * H * e
+            tf = timeit(lambda: K2._edge_softmax_fwd(g._graph, z))
+            tb = timeit(lambda: K2._edge_softmax_bwd(g._graph, a, gr))
+            print(json.dumps({"shape": args.shape, "edges": e, "H": H, "order": args.order, "degree": args.degree,
+                              "edge_softmax_fwd": {"ms": round(tf, 4), "gbs": round(Bf / tf / 1e6), "frac": round(Bf / tf / 1e6 / peak, 3)},
+                              "edge_softmax_bwd": {"ms": round(tb, 4), "gbs": round(Bb / tb / 1e6), "frac": round(Bb / tb / 1e6 / peak, 3)}}),
+                  flush=True)
 
 
 if __name__ == "__main__":
