@@ -169,7 +169,7 @@ __device__ __forceinline__ void store_feat_tile(const GatParams& p, float (&acc)
 
 // ------------------------------------------------------------------ forward
 template <int VEC, int CH, int HT, int UT, bool HUB>
-__global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatParams p) {
+__global__ void __launch_bounds__(kBlockThreads, UT == 4 ? 3 : 2) gat_fwd_kernel(const GatParams p) {
   constexpr int U = UT / CH > 0 ? UT / CH : 1;
   __shared__ __align__(16) float s_w[(kBlockThreads + 32) * HT];  // [group][edge slot][head] weights
   extern __shared__ __align__(16) unsigned char smem_raw[];       // hub rows only
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kBlockThreads, 2) gat_fwd_kernel(const GatPara
 // SRC_PASS = true : CSR over src rows u.  neighbour = dst v: gathers dZ[v] (owner: row_pack[v,:]); own row: ft[u].
 //            outputs grad_ft[u,:], grad_el[u,h].
 template <int VEC, int CH, int HT, int UT, bool SRC_PASS, bool HUB>
-__global__ void __launch_bounds__(kBlockThreads, 2) gat_bwd_kernel(const GatParams p) {
+__global__ void __launch_bounds__(kBlockThreads, UT == 4 ? 3 : 2) gat_bwd_kernel(const GatParams p) {
   constexpr int U = UT / CH > 0 ? UT / CH : 1;
   __shared__ __align__(16) float s_w[(kBlockThreads + 32) * HT * 2];  // [group][edge slot][head]{a*drop, a*drop*g}
   extern __shared__ __align__(16) unsigned char smem_raw[];
