@@ -124,6 +124,19 @@ int32_t dglb_default_row_hub_threshold(int64_t out_len) {
   return (int32_t)t;
 }
 
+int32_t dglb_default_softmax_hub_threshold(int64_t n_heads) {
+  // a hub segment is walked by one warp whose lanes are (edge slot, head): ~32 trips per pass
+  int64_t hp = 1;
+  while (hp < n_heads && hp < 32) hp <<= 1;
+  int64_t t = 1024 / hp;
+  if (t < 64) t = 64;
+  return (int32_t)t;
+}
+
+size_t dglb_edge_softmax_workspace_bytes(int64_t n_seg, int64_t n_hub, int64_t n_heads) {
+  return edge_softmax_workspace_bytes(n_seg, n_hub, n_heads);
+}
+
 int32_t dglb_default_hub_threshold(int64_t out_len) {
   // A row-task is a chain of dependent batches (G edges per round trip), so its duration is set by its
   // EDGE count, not its bytes: measured on a power-law reddit graph the best cut-off is ~160-400 edges
@@ -141,7 +154,7 @@ int32_t dglb_default_hub_threshold(int64_t out_len) {
 int dglb_gspmm_csr(int op, int reduce, int dtype, int64_t n_rows, int64_t n_cols, int64_t nnz,
                    const int32_t* indptr, const int32_t* indices, const int32_t* eids, const void* ufeat,
                    const void* efeat, int ndim, const int64_t* lhs_shape_host, const int64_t* rhs_shape_host,
-                   void* out, int32_t* arg_u, int32_t* arg_e, const float* row_scale, int accumulate,
+                   void* out, int32_t* arg_u, int32_t* arg_e, const float* row_scale, int flags,
                    const dglb_hub_t* hub, void* stream) {
   DGLB_CHECK_ARG(valid_op(op, false), "gspmm: unknown op %d", op);
   DGLB_CHECK_ARG(reduce >= DGLB_REDUCE_SUM && reduce <= DGLB_REDUCE_MIN, "gspmm: unknown reducer %d", reduce);
@@ -150,7 +163,9 @@ int dglb_gspmm_csr(int op, int reduce, int dtype, int64_t n_rows, int64_t n_cols
   DGLB_CHECK_ARG(indptr && (indices || nnz == 0) && out, "gspmm: null graph/out pointer");
   DGLB_CHECK_ARG(op == DGLB_OP_COPY_RHS || ufeat || nnz == 0, "gspmm: op needs lhs (node) data");
   DGLB_CHECK_ARG(op == DGLB_OP_COPY_LHS || efeat || nnz == 0, "gspmm: op needs rhs (edge) data");
-  DGLB_CHECK_ARG(!accumulate || reduce == DGLB_REDUCE_SUM, "gspmm: accumulate is only defined for reducer sum");
+  DGLB_CHECK_ARG((flags & ~(DGLB_SPMM_ACCUMULATE | DGLB_SPMM_ZERO_INF)) == 0, "gspmm: unknown flag bits %d", flags);
+  DGLB_CHECK_ARG(!(flags & DGLB_SPMM_ACCUMULATE) || reduce == DGLB_REDUCE_SUM,
+                 "gspmm: accumulate is only defined for reducer sum");
   BcastShape b;
   int64_t rs;
   int rc = make_bcast(op, ndim, lhs_shape_host, rhs_shape_host, &b, &rs);
@@ -158,11 +173,11 @@ int dglb_gspmm_csr(int op, int reduce, int dtype, int64_t n_rows, int64_t n_cols
   if (op == DGLB_OP_COPY_LHS) { for (int d = 0; d < b.ndim; ++d) { b.rhs[d] = b.lhs[d]; b.out[d] = b.lhs[d]; } b.rhs_len = b.out_len = b.lhs_len; }
   if (op == DGLB_OP_COPY_RHS) { for (int d = 0; d < b.ndim; ++d) { b.lhs[d] = b.rhs[d]; b.out[d] = b.rhs[d]; } b.lhs_len = b.out_len = b.rhs_len; }
   if (dtype == DGLB_BF16)
-    return spmm_csr_bf16(op, reduce, n_rows, indptr, indices, ufeat, b.out_len, out, row_scale, accumulate, hub,
+    return spmm_csr_bf16(op, reduce, n_rows, indptr, indices, ufeat, b.out_len, out, row_scale, flags, hub,
                          static_cast<cudaStream_t>(stream));
   return spmm_csr_f32(op, reduce, n_rows, n_cols, nnz, indptr, indices, eids, static_cast<const float*>(ufeat),
                       static_cast<const float*>(efeat), b, static_cast<float*>(out), arg_u, arg_e, row_scale,
-                      accumulate, hub, static_cast<cudaStream_t>(stream));
+                      flags, hub, static_cast<cudaStream_t>(stream));
 }
 
 static int sddmm_common(int op, int dtype, int lhs_target, int rhs_target, int ndim, const int64_t* ls,
@@ -231,30 +246,24 @@ int dglb_gsddmm_coo(int op, int dtype, int lhs_target, int rhs_target, int64_t n
 
 int dglb_edge_softmax_fwd(int dtype, int64_t n_dst, int64_t nnz, int64_t n_heads, const int32_t* indptr,
                           const int32_t* eids, const void* logits, void* out, const dglb_hub_t* hub, void* stream) {
-  const int32_t* hub_rows = hub ? hub->rows : nullptr;
-  const int32_t n_hub = hub ? hub->n_hub : 0;
-  const int32_t hub_threshold = hub ? hub->threshold : 0;
   if (dtype != DGLB_F32) { set_error("edge_softmax: only f32 is implemented"); return DGLB_E_UNSUPPORTED; }
   DGLB_CHECK_ARG(n_dst >= 0 && nnz >= 0 && n_heads >= 0 && indptr, "edge_softmax_fwd: bad sizes / null indptr");
   DGLB_CHECK_ARG(nnz == 0 || (logits && out), "edge_softmax_fwd: null data");
   if (nnz == 0) return DGLB_OK;
-  return edge_softmax_f32(false, n_dst, n_heads, indptr, eids, static_cast<const float*>(logits), nullptr,
-                          static_cast<float*>(out), hub_rows, n_hub, hub_threshold, static_cast<cudaStream_t>(stream));
+  return edge_softmax_f32(false, n_dst, nnz, n_heads, indptr, eids, static_cast<const float*>(logits), nullptr,
+                          static_cast<float*>(out), hub, static_cast<cudaStream_t>(stream));
 }
 
 int dglb_edge_softmax_bwd(int dtype, int64_t n_dst, int64_t nnz, int64_t n_heads, const int32_t* indptr,
                           const int32_t* eids, const void* out, const void* grad_out, void* grad_logits,
                           const dglb_hub_t* hub, void* stream) {
-  const int32_t* hub_rows = hub ? hub->rows : nullptr;
-  const int32_t n_hub = hub ? hub->n_hub : 0;
-  const int32_t hub_threshold = hub ? hub->threshold : 0;
   if (dtype != DGLB_F32) { set_error("edge_softmax: only f32 is implemented"); return DGLB_E_UNSUPPORTED; }
   DGLB_CHECK_ARG(n_dst >= 0 && nnz >= 0 && n_heads >= 0 && indptr, "edge_softmax_bwd: bad sizes / null indptr");
   DGLB_CHECK_ARG(nnz == 0 || (out && grad_out && grad_logits), "edge_softmax_bwd: null data");
   if (nnz == 0) return DGLB_OK;
-  return edge_softmax_f32(true, n_dst, n_heads, indptr, eids, static_cast<const float*>(out),
-                          static_cast<const float*>(grad_out), static_cast<float*>(grad_logits), hub_rows, n_hub,
-                          hub_threshold, static_cast<cudaStream_t>(stream));
+  return edge_softmax_f32(true, n_dst, nnz, n_heads, indptr, eids, static_cast<const float*>(out),
+                          static_cast<const float*>(grad_out), static_cast<float*>(grad_logits), hub,
+                          static_cast<cudaStream_t>(stream));
 }
 
 static void gat_zero(GatParams& p) { memset(&p, 0, sizeof(p)); }

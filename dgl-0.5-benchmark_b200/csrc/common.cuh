@@ -62,6 +62,8 @@ __device__ __forceinline__ FVec<VEC> ldg_vec(const float* p) {
   return r;
 }
 
+
+
 template <int VEC>
 __device__ __forceinline__ void st_vec(float* p, const FVec<VEC>& r) {
   if constexpr (VEC == 4) {

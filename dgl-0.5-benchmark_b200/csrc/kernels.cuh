@@ -73,9 +73,9 @@ int sddmm_csr_fast_f32(int op, int64_t n_dst, const int32_t* indptr, const int32
                        int dtype = DGLB_F32);
 int sddmm_generic_f32(const GenericSddmmParams& g, cudaStream_t stream);
 // edge_softmax.cu
-int edge_softmax_f32(bool bwd, int64_t n_dst, int64_t n_heads, const int32_t* indptr, const int32_t* eids,
-                     const float* a, const float* b, float* out, const int32_t* hub_rows, int32_t n_hub,
-                     int32_t hub_threshold, cudaStream_t stream);
+int edge_softmax_f32(bool bwd, int64_t n_dst, int64_t nnz, int64_t n_heads, const int32_t* indptr, const int32_t* eids,
+                     const float* a, const float* b, float* out, const dglb_hub_t* hub, cudaStream_t stream);
+size_t edge_softmax_workspace_bytes(int64_t n_seg, int64_t n_hub, int64_t n_heads);
 // gat_fused.cu  (which: 0 fwd, 1 bwd_dst, 2 bwd_src)
 int gat_fused_f32(int which, GatParams& p, int64_t H, int64_t F, float dropout_p, uint64_t seed,
                   int32_t n_hub, int32_t hub_threshold, cudaStream_t stream);

@@ -30,7 +30,9 @@
 
 namespace dglb {
 
-enum : int { RMODE_NONE = 0, RMODE_FULL = 1, RMODE_HEAD = 2 };
+// how the edge operand W is indexed: not at all / same width as the output / one value per head
+// (column k reads W[e, k / inner]) / ONE scalar per edge (rhs_len == 1: GCN / RGCN edge weights).
+enum : int { RMODE_NONE = 0, RMODE_FULL = 1, RMODE_HEAD = 2, RMODE_SCALAR = 3 };
 
 struct SpmmParams {
   const int32_t* __restrict__ indptr;
@@ -57,6 +59,7 @@ struct SpmmParams {
   int G, log2G;
   int hub_threshold;
   int accumulate;  // sum only: add the result to the existing contents of `out`
+  int zero_inf;    // max/min only: store 0 where the result is +-inf (empty rows), as upstream's Python does
 };
 
 template <int VEC, int CH, int RED>
@@ -76,15 +79,21 @@ struct Acc {
   }
 };
 
-template <int RED>
+// TU / TE: track the source-node / edge-id argument.  Upstream records arg_u only when the op reads
+// the node operand and arg_e only when it reads the edge operand; an untracked argument stays 0 and
+// costs no registers (copy_u_max: 98 -> 80 registers per thread).
+template <int RED, bool TU = true, bool TE = true>
 __device__ __forceinline__ void combine(float& acc, int32_t& au, int32_t& ae, float val, int32_t c,
                                         int32_t e) {
   if constexpr (RED == DGLB_REDUCE_SUM) {
     acc = __fadd_rn(acc, val);
-  } else if constexpr (RED == DGLB_REDUCE_MAX) {
-    if (acc < val) { acc = val; au = c; ae = e; }
   } else {
-    if (acc > val) { acc = val; au = c; ae = e; }
+    const bool better = RED == DGLB_REDUCE_MAX ? (acc < val) : (acc > val);
+    if (better) {
+      acc = val;
+      if constexpr (TU) au = c;
+      if constexpr (TE) ae = e;
+    }
   }
 }
 
@@ -95,10 +104,14 @@ template <int VEC, int CH, int OP, int RED, int RMODE, typename T = float>
 __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0, int n, int nmax,
                                                  int lg, int tile0, Acc<VEC, CH, RED>& acc) {
   static_assert(sizeof(T) == 4 || RMODE == RMODE_NONE, "bf16 storage is implemented for copy_lhs");
-  constexpr int U = 8 / CH;
+  // neighbour rows per load batch: 8 chunks in flight per lane; two-operand gathers (mul with a
+  // per-column or per-head W) stage twice as much per row, so they batch half as many rows
+  constexpr int U = (OP == DGLB_OP_MUL && (RMODE == RMODE_FULL || RMODE == RMODE_HEAD)) ? (CH >= 4 ? 1 : 4 / CH) : 8 / CH;
   constexpr bool USE_L = OP != DGLB_OP_COPY_RHS;
   constexpr bool USE_R = OP != DGLB_OP_COPY_LHS;
-  constexpr bool NEED_E = USE_R || RED != DGLB_REDUCE_SUM;
+  constexpr bool TRACK_U = RED != DGLB_REDUCE_SUM && USE_L;
+  constexpr bool TRACK_E = RED != DGLB_REDUCE_SUM && USE_R;
+  constexpr bool NEED_E = USE_R;
   const int G = p.G;
   bool colv[CH];
   int k[CH], hk[CH];
@@ -112,10 +125,14 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0
   for (int off = 0; off < nmax; off += G) {
     const int m = min(max(n - off, 0), G);
     int my_c = 0, my_e = 0;
+    float my_w = 0.f;
     if (lg < m) {
       const int64_t j = j0 + off + lg;
-      if (USE_L || RED != DGLB_REDUCE_SUM) my_c = __ldg(p.indices + j);
+      if (USE_L) my_c = __ldg(p.indices + j);
       if (NEED_E) my_e = p.eids ? __ldg(p.eids + j) : (int)j;
+      // scalar edge weights ride along with the indices: one load per lane per G neighbours, then a
+      // shuffle broadcast, instead of one (uniform-address) load per lane per neighbour
+      if constexpr (RMODE == RMODE_SCALAR) my_w = __ldg(p.W + my_e);
     }
     const int mmax = min(G, nmax - off);
     for (int t = 0; t < mmax; t += U) {
@@ -124,8 +141,8 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0
       FVec<(VEC > 4 ? 4 : VEC)> wv[U][CH];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        cc[u] = __shfl_sync(FULL_MASK, my_c, t + u, G);
-        ee[u] = NEED_E ? __shfl_sync(FULL_MASK, my_e, t + u, G) : 0;
+        cc[u] = USE_L ? __shfl_sync(FULL_MASK, my_c, t + u, G) : 0;
+        ee[u] = (NEED_E && (RMODE != RMODE_SCALAR || TRACK_E)) ? __shfl_sync(FULL_MASK, my_e, t + u, G) : 0;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -145,13 +162,16 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const bool valid = (t + u) < m;
+        float ws = 0.f;
+        if constexpr (RMODE == RMODE_SCALAR) ws = __shfl_sync(FULL_MASK, my_w, t + u, G);
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           if (valid && colv[c]) {
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
               float val;
-              const float w = (RMODE == RMODE_HEAD) ? wv[u][c].v[0] : (USE_R ? wv[u][c].v[v] : 0.f);
+              const float w = (RMODE == RMODE_SCALAR) ? ws
+                              : (RMODE == RMODE_HEAD) ? wv[u][c].v[0] : (USE_R ? wv[u][c].v[v] : 0.f);
               if constexpr (OP == DGLB_OP_COPY_LHS) val = xv[u][c].at(v);
               else if constexpr (OP == DGLB_OP_COPY_RHS) val = w;
               else if constexpr (OP == DGLB_OP_MUL) val = __fmul_rn(xv[u][c].at(v), w);
@@ -159,7 +179,7 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0
               if constexpr (RED == DGLB_REDUCE_SUM) {
                 acc.a[c][v] = __fadd_rn(acc.a[c][v], val);
               } else {
-                combine<RED>(acc.a[c][v], acc.au[c][v], acc.ae[c][v], val, cc[u], ee[u]);
+                combine<RED, TRACK_U, TRACK_E>(acc.a[c][v], acc.au[c][v], acc.ae[c][v], val, cc[u], ee[u]);
               }
             }
           }
@@ -170,8 +190,21 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0
 }
 
 // ------------------------------------------------------------------ row-per-group kernel
+// Residency matters more than anything else here: the same copy_u_sum kernel ran 2.72 ms at 70
+// registers (3 CTAs / SM) and 4.78 ms at 84 registers (2 CTAs / SM) on the products graph, and
+// copy_u_max went from 4.04 ms (98 registers) to 2.88 ms (80).  The max/min and scalar-weight variants
+// are therefore held to 80 registers (except the widest tiles, which would spill in the gather loop).
+// The copy/sum variants already fit and keep ptxas' own allocation (0 = no minimum): forcing the bound
+// on them made ptxas start consuming the first gathered row before the last one was issued.
+template <int OP, int RED>
+constexpr int spmm_min_ctas(int rmode, int ch, int vec) {
+  if (RED != DGLB_REDUCE_SUM) return ch * vec >= 16 ? 0 : 3;
+  if (rmode == RMODE_SCALAR) return vec == 4 ? 3 : 0;  // what keeps the 8 gathers of a batch together (SASS-checked)
+  return 0;
+}
+
 template <int VEC, int CH, int OP, int RED, int RMODE, typename T = float>
-__global__ void __launch_bounds__(kBlockThreads)
+__global__ void __launch_bounds__(kBlockThreads, spmm_min_ctas<OP, RED>(RMODE, CH, VEC))
 spmm_rows_kernel(const SpmmParams p) {
   const int G = p.G;
   const int lg = threadIdx.x & (G - 1);
@@ -205,6 +238,11 @@ spmm_rows_kernel(const SpmmParams p) {
               const FVec<VEC> prev = ldg_vec_t<T, VEC>(reinterpret_cast<const T*>(p.out) + off);
 #pragma unroll
               for (int v = 0; v < VEC; ++v) o.v[v] = __fadd_rn(prev.v[v], o.v[v]);
+            }
+          } else {
+            if (p.zero_inf) {
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) o.v[v] = isinf(o.v[v]) ? 0.f : o.v[v];
             }
           }
           st_vec_t<T, VEC>(reinterpret_cast<T*>(p.out) + off, o);
@@ -307,6 +345,8 @@ __global__ void __launch_bounds__(kBlockThreads) spmm_hub_combine_kernel(const S
   if (p.row_scale) a = __fdiv_rn(a, __ldg(p.row_scale + row));
   if constexpr (RED == DGLB_REDUCE_SUM) {
     if (p.accumulate) a = __fadd_rn(load_scalar_t<T>(reinterpret_cast<const T*>(p.out) + off), a);
+  } else {
+    if (p.zero_inf && isinf(a)) a = 0.f;
   }
   store_scalar_t<T>(reinterpret_cast<T*>(p.out) + off, a);
   if constexpr (RED != DGLB_REDUCE_SUM) {
@@ -328,7 +368,7 @@ struct GenericSpmmParams {
   const float* row_scale;
   int64_t n_rows;
   int op, red;
-  int accumulate;
+  int accumulate, zero_inf;
   BcastShape b;
 };
 
@@ -374,6 +414,7 @@ __global__ void __launch_bounds__(kBlockThreads) spmm_generic_kernel(const Gener
   }
   if (p.row_scale) acc = __fdiv_rn(acc, p.row_scale[row]);
   if (p.accumulate) acc = __fadd_rn(p.out[idx], acc);
+  if (p.zero_inf && p.red != DGLB_REDUCE_SUM && isinf(acc)) acc = 0.f;
   p.out[idx] = acc;
   if (p.red != DGLB_REDUCE_SUM) {
     if (p.arg_u) p.arg_u[idx] = au;
@@ -439,7 +480,7 @@ static int and_vec(int a, int b) { return a < b ? a : b; }
 int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz,
                  const int32_t* indptr, const int32_t* indices, const int32_t* eids, const float* X,
                  const float* W, const BcastShape& b, float* out, int32_t* arg_u, int32_t* arg_e,
-                 const float* row_scale, int accumulate, const dglb_hub_t* hub, cudaStream_t stream) {
+                 const float* row_scale, int flags, const dglb_hub_t* hub, cudaStream_t stream) {
   (void)n_cols;
   (void)nnz;
   if (n_rows == 0 || b.out_len == 0) return DGLB_OK;
@@ -494,10 +535,12 @@ int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz
     }
     p.n_rows = n_rows; p.D = (int)b.out_len; p.rhs_len = (int)b.rhs_len; p.inner = (int)inner;
     p.hub_threshold = use_hub ? hub->threshold : INT32_MAX;
-    p.accumulate = accumulate;
+    p.accumulate = (flags & DGLB_SPMM_ACCUMULATE) ? 1 : 0;
+    p.zero_inf = (flags & DGLB_SPMM_ZERO_INF) ? 1 : 0;
     int vec = pick_vec(b.out_len, out);
     if (use_l) vec = and_vec(vec, pick_vec(b.out_len, X));
     if (rmode == RMODE_FULL) vec = and_vec(vec, pick_vec(b.out_len, W));
+    if (rmode == RMODE_HEAD && b.rhs_len == 1) rmode = RMODE_SCALAR;
     if (rmode == RMODE_HEAD) { while (inner % vec) vec >>= 1; }
     if (reduce != DGLB_REDUCE_SUM) {
       if (arg_u) vec = and_vec(vec, pick_vec(b.out_len, arg_u));
@@ -506,13 +549,16 @@ int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz
     if (op == DGLB_OP_COPY_LHS) return dispatch_red<DGLB_OP_COPY_LHS, RMODE_NONE>(p, reduce, vec, n_hub, n_seg, stream);
     if (op == DGLB_OP_COPY_RHS) return dispatch_red<DGLB_OP_COPY_RHS, RMODE_FULL>(p, reduce, vec, n_hub, n_seg, stream);
     if (rmode == RMODE_FULL) return dispatch_vec_ch<DGLB_OP_MUL, DGLB_REDUCE_SUM, RMODE_FULL>(p, vec, n_hub, n_seg, stream);
+    if (rmode == RMODE_SCALAR) return dispatch_vec_ch<DGLB_OP_MUL, DGLB_REDUCE_SUM, RMODE_SCALAR>(p, vec, n_hub, n_seg, stream);
     return dispatch_vec_ch<DGLB_OP_MUL, DGLB_REDUCE_SUM, RMODE_HEAD>(p, vec, n_hub, n_seg, stream);
   }
   // ---- generic path
   GenericSpmmParams g;
   g.indptr = indptr; g.indices = indices; g.eids = eids; g.X = X; g.W = W; g.out = out;
   g.arg_u = arg_u; g.arg_e = arg_e; g.row_scale = row_scale; g.n_rows = n_rows;
-  g.op = op; g.red = reduce; g.b = b; g.accumulate = accumulate;
+  g.op = op; g.red = reduce; g.b = b;
+  g.accumulate = (flags & DGLB_SPMM_ACCUMULATE) ? 1 : 0;
+  g.zero_inf = (flags & DGLB_SPMM_ZERO_INF) ? 1 : 0;
   (void)use_r;
   const int64_t total = n_rows * b.out_len;
   const int64_t blocks = (total + kBlockThreads - 1) / kBlockThreads;
@@ -536,7 +582,8 @@ int spmm_csr_bf16(int op, int reduce, int64_t n_rows, const int32_t* indptr, con
   p.indptr = indptr; p.indices = indices; p.eids = nullptr;
   p.X = static_cast<const float*>(X); p.W = nullptr; p.out = static_cast<float*>(out);
   p.arg_u = nullptr; p.arg_e = nullptr; p.row_scale = row_scale;
-  p.n_rows = n_rows; p.D = (int)D; p.rhs_len = 0; p.inner = 1; p.accumulate = accumulate;
+  p.n_rows = n_rows; p.D = (int)D; p.rhs_len = 0; p.inner = 1;
+  p.accumulate = (accumulate & DGLB_SPMM_ACCUMULATE) ? 1 : 0; p.zero_inf = 0;
   const bool use_hub = hub && hub->n_hub > 0 && hub->n_seg > 0 && hub->rows && hub->seg_ptr && hub->seg_hub &&
                        hub->seg_len > 0;
   const int n_hub = use_hub ? hub->n_hub : 0, n_seg = use_hub ? hub->n_seg : 0;

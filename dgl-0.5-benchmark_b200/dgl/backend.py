@@ -40,8 +40,8 @@ def _expand(x, shape):
 
 class GSpMM(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, gidx, op, reduce_op, X, Y, row_scale):
-        out, (argX, argY) = K._gspmm(gidx, op, reduce_op, X, Y, row_scale)
+    def forward(ctx, gidx, op, reduce_op, X, Y, row_scale, zero_inf=False):
+        out, (argX, argY) = K._gspmm(gidx, op, reduce_op, X, Y, row_scale, zero_inf=zero_inf)
         ctx.backward_cache = gidx, op, reduce_op
         ctx.has_scale = row_scale is not None
         ctx.save_for_backward(X, Y, argX, argY, row_scale)
@@ -86,7 +86,7 @@ class GSpMM(torch.autograd.Function):
                 else:
                     dY.scatter_add_(0, argY.long(), dZ)
             dY = _reduce_grad(dY, Y.shape)
-        return None, None, None, dX, dY, None
+        return None, None, None, dX, dY, None, None
 
 
 class GSDDMM(torch.autograd.Function):
@@ -178,12 +178,14 @@ class GATFused(torch.autograd.Function):
         return None, grad_ft, grad_el, grad_er, None, None, None
 
 
-def gspmm(gidx, op, reduce_op, lhs_data, rhs_data, row_scale=None):
+def gspmm(gidx, op, reduce_op, lhs_data, rhs_data, row_scale=None, zero_inf=False):
+    """zero_inf (max / min): rows without in-edges come back as 0 instead of -/+inf (the replacement
+    upstream's dgl.ops.gspmm applies afterwards, done in the kernel's store instead of two more passes)."""
     if op == "sub":
         op, rhs_data = "add", -rhs_data
     if op == "div":
         op, rhs_data = "mul", 1.0 / rhs_data
-    return GSpMM.apply(gidx, op, reduce_op, lhs_data, rhs_data, row_scale)
+    return GSpMM.apply(gidx, op, reduce_op, lhs_data, rhs_data, row_scale, zero_inf)
 
 
 def gsddmm(gidx, op, lhs_data, rhs_data, lhs_target="u", rhs_target="v"):

@@ -49,10 +49,9 @@ def gspmm(g, op, reduce_op, lhs_data, rhs_data):
         if gidx.n_edges == 0:
             return B.gspmm(gidx, op, "sum", lhs_data, rhs_data)
         return B.gspmm(gidx, op, "sum", lhs_data, rhs_data, gidx.csc().mean_divisor())
-    ret = B.gspmm(gidx, op, reduce_op, lhs_data, rhs_data)
-    if reduce_op in ("min", "max"):
-        ret = torch.where(torch.isinf(ret), torch.zeros((), dtype=ret.dtype, device=ret.device), ret)
-    return ret
+    # max / min: upstream replaces +-inf (nodes without in-edges) by 0 in a Python post-pass; here the
+    # kernel's store does it (flag DGLB_SPMM_ZERO_INF), saving two full passes over the output
+    return B.gspmm(gidx, op, reduce_op, lhs_data, rhs_data, zero_inf=reduce_op in ("min", "max"))
 
 
 def _attach_shorthands():

@@ -96,12 +96,14 @@ def _dtype_code(what, bf16_ok, *ts):
     raise DGLError("%s: operands must be all float32 (or all bfloat16 where supported); got %s" % (what, sorted(map(str, dts))))
 
 
-def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None):
+def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None, zero_inf=False):
     """out[v] = reduce_{(s->v)} op(u[s], e[eid]).  Returns (out, (arg_u, arg_e)).
 
     `gidx` is a GraphIndex; the kernel walks its CSC.  reduce_op in {sum, max, min}; `row_scale`
     (float32, n_dst) fuses the mean divide.  arg_u / arg_e (graph idtype) only for max / min.
     `out` (reducer sum only): accumulate into this existing tensor instead of allocating a result.
+    `zero_inf` (max / min): store 0 instead of -/+inf (rows without in-edges), i.e. upstream's
+    where(isinf(out), 0, out) post-pass folded into the kernel's store.
     """
     use_u = op != "copy_rhs"
     use_e = op != "copy_lhs"
@@ -175,7 +177,7 @@ def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None):
                               _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(csc.eids),
                               _capi.ptr(u), _capi.ptr(e), ndim, ls, rs,
                               _capi.ptr(v), _capi.ptr(arg_u), _capi.ptr(arg_e), _capi.ptr(row_scale),
-                              1 if out is not None else 0, hub, stream)
+                              (1 if out is not None else 0) | (2 if (zero_inf and use_cmp) else 0), hub, stream)
         _capi.check(rc, "dglb_gspmm_csr")
         _capi.count_launch(1 + hub_launches)
         if use_cmp and gidx.idtype != torch.int32:
@@ -263,6 +265,18 @@ def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
     return out
 
 
+def _softmax_hub_arg(csc, heads, dev):
+    """Hub-row segments + workspace for edge_softmax: (ctypes pointer or None, keep-alive, launches)."""
+    thr = int(HUB_THRESHOLD) if HUB_THRESHOLD is not None else _capi.lib().dglb_default_softmax_hub_threshold(int(heads))
+    info = csc.hubs(thr)
+    if info is None or heads > 32:
+        return None, None, 0
+    nbytes = _capi.lib().dglb_edge_softmax_workspace_bytes(info.n_seg, info.n_hub, int(heads))
+    ws = torch.empty(max(1, nbytes // 4), dtype=torch.float32, device=dev)
+    st = info.struct(ws)
+    return ctypes.byref(st), (st, ws), 3
+
+
 def _edge_softmax_fwd(gidx, logits):
     """softmax over each destination's in-edges; logits (E, ...) in edge-id order."""
     _check_float32(logits)
@@ -276,8 +290,7 @@ def _edge_softmax_fwd(gidx, logits):
     heads = logits.numel() // gidx.n_edges
     csc = gidx.csc()
     l = _capi.lib()
-    thr = _hub_threshold(max(heads, 64), row_cta=True)
-    hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
+    hub, _keep, hub_launches = _softmax_hub_arg(csc, heads, dev)
     stream = _capi.enter(dev)
     rc = l.dglb_edge_softmax_fwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(csc.eids),
                                  _capi.ptr(logits), _capi.ptr(out), hub, stream)
@@ -297,8 +310,7 @@ def _edge_softmax_bwd(gidx, out, grad_out):
     heads = out.numel() // gidx.n_edges
     csc = gidx.csc()
     l = _capi.lib()
-    thr = _hub_threshold(max(heads, 64), row_cta=True)
-    hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
+    hub, _keep, hub_launches = _softmax_hub_arg(csc, heads, dev)
     stream = _capi.enter(dev)
     rc = l.dglb_edge_softmax_bwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(csc.eids),
                                  _capi.ptr(out), _capi.ptr(grad_out), _capi.ptr(grad), hub, stream)

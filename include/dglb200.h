@@ -110,17 +110,21 @@ int dglb_csr_find_hub_rows(int64_t n_rows, const int32_t* indptr, int32_t thresh
                            int32_t* hub_rows, int64_t cap, int32_t* n_hub, void* stream);
 /* thresholds the library recommends for a given feature width (elements): the first for the
  * segmented hub path of gspmm / gsddmm (64-256 edges: a row-task's duration follows its edge count),
- * the second for the one-CTA-per-hub-row path of edge_softmax and the fused GAT kernels (only real
- * hubs: ~1.5 MB of gather per row-task, 256-8192 edges) */
+ * the second for the one-CTA-per-hub-row path of the fused GAT kernels (only real hubs: ~1.5 MB of
+ * gather per row-task, 256-8192 edges), the third for the segmented hub path of edge_softmax
+ * (64-1024 edges by head count: one warp walks a segment in ~32 trips per pass) */
 int32_t dglb_default_hub_threshold(int64_t out_len);
 int32_t dglb_default_row_hub_threshold(int64_t out_len);
+int32_t dglb_default_softmax_hub_threshold(int64_t n_heads);
 
 /* Hub-row metadata handed to the compute entry points (NULL = treat every row as an ordinary row).
  * Rows with nnz > threshold are skipped by the row-per-group kernels.  gspmm / gsddmm cut each hub
  * row into segments of at most seg_len entries, one CTA per segment, so a 20 000-edge hub is spread
  * over many SMs; gspmm writes per-segment partial results to `workspace` and a second kernel
  * combines the segments of a row in segment order (deterministic, no atomics; max/min ties still
- * resolve to the first CSR entry).  edge_softmax and the fused GAT kernels use one CTA per hub row.
+ * resolve to the first CSR entry).  edge_softmax uses the same segments (a warp per segment, three
+ * launches: segment stats, per-row combine, apply; workspace dglb_edge_softmax_workspace_bytes).
+ * The fused GAT kernels use one CTA per hub row.
  *   rows     [n_hub]    hub row ids
  *   seg_ptr  [n_hub+1]  first segment of each hub row (prefix sum of ceil(nnz/seg_len))
  *   seg_hub  [n_seg]    index into rows[] of the hub row a segment belongs to
@@ -148,23 +152,28 @@ size_t dglb_hub_workspace_bytes(int64_t n_seg, int64_t out_len, int with_args);
  *  - sum: `out` is fully written (empty rows -> 0), callers need not zero it.
  *  - max/min: strict compare in row order => the FIRST entry in CSR order wins ties;
  *    arg_u[r,k] = indices[j*], arg_e[r,k] = eid(j*) (either may be NULL); empty rows ->
- *    out = -/+inf, args = 0 (the Python layer replaces the infinities by 0, as upstream
- *    python/dgl/ops/spmm.py does).
+ *    out = -/+inf, args = 0 -- or out = 0 with DGLB_SPMM_ZERO_INF, which folds upstream's Python
+ *    post-pass (python/dgl/ops/spmm.py: where(isinf(out), 0, out)) into the store.  arg_u is
+ *    recorded only when the op reads the node operand, arg_e only when it reads the edge operand
+ *    (what upstream allocates); the other one, if passed, is filled with 0.
  *  - row_scale (may be NULL): fused epilogue out[r,:] = out[r,:] / row_scale[r] (IEEE division),
  *    used for reducer "mean" with row_scale = float(clamp(in_deg,1)).
- *  - accumulate != 0 (reducer sum only): out[r,:] += result instead of out[r,:] = result; lets a
- *    row-partitioned caller aggregate one source shard at a time while the next shard is in flight.
+ *  - flags: bit mask.  DGLB_SPMM_ACCUMULATE (reducer sum only): out[r,:] += result instead of
+ *    out[r,:] = result; lets a row-partitioned caller aggregate one source shard at a time while the
+ *    next shard is in flight.  DGLB_SPMM_ZERO_INF (max/min only): see above.
  *  - hub (may be NULL): rows listed there (nnz > hub->threshold) are processed by the segmented
  *    split-row path instead of the row-per-group path; the list must come from
  *    dglb_csr_find_hub_rows(indptr, hub->threshold).
  */
+#define DGLB_SPMM_ACCUMULATE 1
+#define DGLB_SPMM_ZERO_INF 2
 int dglb_gspmm_csr(int op, int reduce, int dtype,
                    int64_t n_rows, int64_t n_cols, int64_t nnz,
                    const int32_t* indptr, const int32_t* indices, const int32_t* eids,
                    const void* ufeat, const void* efeat,
                    int ndim, const int64_t* lhs_shape_host, const int64_t* rhs_shape_host,
                    void* out, int32_t* arg_u, int32_t* arg_e,
-                   const float* row_scale, int accumulate,
+                   const float* row_scale, int flags,
                    const dglb_hub_t* hub,
                    void* stream);
 
@@ -200,11 +209,15 @@ int dglb_gsddmm_coo(int op, int dtype, int lhs_target, int rhs_target,
 
 /* ---------------------------------------------------------------- edge_softmax (norm_by='dst')
  * replaces the 4+1 (fwd) / 2+2 (bwd) launch composite of upstream
- * python/dgl/backend/pytorch/sparse.py::EdgeSoftmax with one kernel each.
+ * python/dgl/backend/pytorch/sparse.py::EdgeSoftmax with one kernel each (plus three small ones
+ * when hub rows are listed).
  *   fwd: out[e,h] = exp(logits[e,h] - max_v) / sum_v  over the in-edges of v = dst[e]
  *   bwd: grad_logits[e,h] = out*g - out * sum_{in(v)} (out*g)
  * logits/out/grad are (E, H) in edge-id order; indptr is the CSC over dst, eids its data.
+ * hub (may be NULL): rows with more than hub->threshold in-edges are processed per SEGMENT; needs the
+ * segment lists and hub->workspace >= dglb_edge_softmax_workspace_bytes(n_seg, n_hub, n_heads).
  */
+size_t dglb_edge_softmax_workspace_bytes(int64_t n_seg, int64_t n_hub, int64_t n_heads);
 int dglb_edge_softmax_fwd(int dtype, int64_t n_dst, int64_t nnz, int64_t n_heads,
                           const int32_t* indptr, const int32_t* eids,
                           const void* logits, void* out,

@@ -21,10 +21,12 @@ def _np(t):
     return None if t is None else t.detach().cpu().numpy()
 
 
-def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None):
+def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None, zero_inf=False):
     prev = out
     out, (au, ae) = R._gspmm(_og(gidx), op, reduce_op, _np(u), _np(e))
     out = torch.from_numpy(np.ascontiguousarray(out))
+    if zero_inf and reduce_op in ("max", "min"):
+        out = torch.where(torch.isinf(out), torch.zeros((), dtype=out.dtype), out)
     if row_scale is not None:
         out = out / row_scale.view((-1,) + (1,) * (out.dim() - 1))
     if prev is not None:

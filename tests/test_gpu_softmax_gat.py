@@ -36,6 +36,27 @@ def test_edge_softmax_forward_backward(oracle, cuda, H, kind, small_hub_threshol
     assert_close_sumscaled(n(zt.grad), wantg, scale, rtol=2e-5, what="edge_softmax bwd")
 
 
+@pytest.mark.parametrize("nn_,ne", [(300, 450), (257, 2100), (64, 6000), (33, 9000)])
+@pytest.mark.parametrize("H", [1, 3, 4, 16, 32])
+def test_edge_softmax_group_shapes(oracle, cuda, nn_, ne, H):
+    """average in-degree 1.5 .. 270: every (lanes per row, register depth) choice of the row kernel,
+    partial last groups, rows longer than the register-resident capacity next to short ones."""
+    og, g, src, dst = graphs(oracle, nn_, nn_, ne, seed=ne + H, kind="powerlaw" if ne > 5000 else "uniform")
+    rng = np.random.default_rng(ne + H)
+    z = (2 * rng.standard_normal((ne, H))).astype(np.float32)
+    want = oracle.edge_softmax(og, z)
+    zt = t(z).requires_grad_(True)
+    got = dgl.ops.edge_softmax(g, zt)
+    np.testing.assert_allclose(n(got), want, rtol=1e-5, atol=1e-30)
+    gout = rng.standard_normal((ne, H)).astype(np.float32)
+    got.backward(t(gout))
+    wantg = oracle.edge_softmax_backward(og, want, gout)
+    acc = np.zeros((nn_, H))
+    np.add.at(acc, dst, np.abs(want * gout).astype(np.float64))
+    scale = np.abs(want) * (np.abs(gout) + acc[dst])
+    assert_close_sumscaled(n(zt.grad), wantg, scale, rtol=2e-5, what="edge_softmax bwd")
+
+
 def test_edge_softmax_norm_by_src(oracle, cuda):
     og, g, src, dst = graphs(oracle, 100, 100, 1500, seed=4)
     z = np.random.default_rng(4).standard_normal((1500, 2)).astype(np.float32)

@@ -200,3 +200,20 @@ def test_int64_graph_ids_and_noncontiguous_inputs(oracle, cuda):
     got = n(dgl.ops.gspmm(g, "copy_lhs", "sum", view, None))
     assert np.array_equal(got, oracle.gspmm(og, "copy_lhs", "sum", n(view), None))
     assert np.array_equal(n(dgl.ops.gsddmm(g64, "dot", Xt, Xt)), n(dgl.ops.gsddmm(g, "dot", Xt, Xt)))
+
+
+def test_zero_inf_flag_is_the_upstream_post_pass(oracle, cuda, small_hub_threshold):
+    """kernel-level _gspmm keeps -/+inf in rows without in-edges (upstream _CAPI_DGLKernelSpMM contract);
+    DGLB_SPMM_ZERO_INF stores what upstream's where(isinf(out), 0, out) would, bit for bit, args untouched."""
+    from dgl import sparse as K
+    og, g, src, dst = graphs(oracle, 3000, 3000, 30000, seed=77, kind="powerlaw")  # hub rows and empty rows
+    X = np.random.default_rng(77).standard_normal((3000, 24)).astype(np.float32)
+    X[5, 3], X[6, 2] = np.inf, -np.inf  # genuine infinities in the data are replaced too (as upstream does)
+    for red in ("max", "min"):
+        raw, (au, _) = K._gspmm(g._graph, "copy_lhs", red, t(X), None)
+        fused, (au2, _) = K._gspmm(g._graph, "copy_lhs", red, t(X), None, zero_inf=True)
+        want_raw, (wu, _) = oracle.gspmm_with_args(og, "copy_lhs", red, X, None)
+        assert np.array_equal(n(raw), want_raw) and np.isinf(n(raw)).any()
+        assert np.array_equal(n(fused), np.where(np.isinf(want_raw), np.float32(0), want_raw))
+        assert np.array_equal(n(au), wu) and np.array_equal(n(au2), wu)
+        assert np.array_equal(n(dgl.ops.gspmm(g, "copy_lhs", red, t(X), None)), n(fused))

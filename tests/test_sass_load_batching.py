@@ -54,3 +54,45 @@ def test_gathers_are_issued_as_a_batch(sass, fragment, min_run):
         elif re.search(r"\b(FFMA|FADD|FMUL)\b", line):
             run = 0
     assert best >= min_run, "%s: longest run of vector gathers before an FP consumer is %d (< %d)" % (fragment, best, min_run)
+
+
+# Residency guard: 256-thread CTAs need <= 80 registers per thread for 3 CTAs per SM.  Measured on the
+# products graph: copy_u_sum 2.72 ms at 70 registers vs 4.78 ms at 84; copy_u_max 4.04 ms at 98 vs 2.88 ms
+# at 80; fused GAT 1.2-1.35x from 2 -> 3 CTAs per SM (profiles/r01_notes.md sections 9-10).
+REG_BUDGET = {
+    "spmm_rows_kernelILi4ELi1ELi4ELi0ELi0EfEE": 80,   # copy_u_sum D=64/128
+    "spmm_rows_kernelILi4ELi2ELi4ELi0ELi0EfEE": 80,   # D=256
+    "spmm_rows_kernelILi2ELi4ELi4ELi0ELi0EfEE": 80,   # D=602
+    "spmm_rows_kernelILi4ELi1ELi4ELi1ELi0EfEE": 80,   # copy_u_max D=64
+    "spmm_rows_kernelILi2ELi4ELi4ELi1ELi0EfEE": 80,   # copy_u_max D=602
+    "spmm_rows_kernelILi4ELi1ELi2ELi0ELi3EfEE": 80,   # u_mul_e_sum with (E,1) weights, D=64
+    "sddmm_dot_kernelILi2ELi4ELi5ELb0ELb0EfEE": 80,   # u_dot_v D=602
+    "gat_fwd_kernelILi4ELi1ELi1ELi4ELb0EEE": 80,      # fused GAT forward, UT = 4
+    "gat_bwd_kernelILi4ELi1ELi1ELi4ELb0ELb0EEE": 80,  # fused GAT backward (dst pass)
+    "gat_bwd_kernelILi4ELi1ELi1ELi4ELb1ELb0EEE": 80,  # fused GAT backward (src pass)
+}
+
+
+@pytest.fixture(scope="module")
+def res_usage(sass):
+    import os
+    lib = os.path.join(ROOT, "dgl-0.5-benchmark_b200", "lib", "libdglb200.so")
+    out = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True, check=True).stdout
+    regs, name = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+)", line)
+        if m and name:
+            regs[name] = int(m.group(1))
+    return regs
+
+
+@pytest.mark.parametrize("fragment,budget", sorted(REG_BUDGET.items()))
+def test_hot_kernels_keep_three_ctas_per_sm(res_usage, fragment, budget):
+    names = [n for n in res_usage if fragment in n]
+    assert names, "kernel %s not found in libdglb200.so" % fragment
+    assert res_usage[names[0]] <= budget, "%s uses %d registers (> %d: only 2 CTAs per SM)" % (
+        fragment, res_usage[names[0]], budget)
