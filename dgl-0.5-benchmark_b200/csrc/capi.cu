@@ -117,11 +117,12 @@ size_t dglb_hub_workspace_bytes(int64_t n_seg, int64_t out_len, int with_args) {
 }
 
 int32_t dglb_default_row_hub_threshold(int64_t out_len) {
-  if (out_len < 1) out_len = 1;
-  int64_t t = (int64_t)(1536 * 1024) / (out_len * 4);
-  if (t < 256) t = 256;
-  if (t > 8192) t = 8192;
-  return (int32_t)t;
+  // One CTA per hub row (fused GAT).  Swept on power-law reddit / products graphs for (H,F) = (1,16), (4,16),
+  // (4,40), (1,64): monotonically faster down to the smallest cut-off tried (profiles/r01_notes.md section 11:
+  // e.g. (1,16) forward 3.61 ms at the old byte-based cut-off of 8192 edges, 0.62 ms at 128) -- a long row on a
+  // 4..32-lane group is a serial chain of gather batches, a CTA splits it 8..64 ways.
+  (void)out_len;
+  return 128;
 }
 
 int32_t dglb_default_softmax_hub_threshold(int64_t n_heads) {

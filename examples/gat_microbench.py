@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--feat", type=int, default=16)
     ap.add_argument("--degree", default="uniform")
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--row-hub", default="", help="comma list of hub cut-offs (edges) to sweep for the FUSED kernels only")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     n, e, _, _ = synthetic.SHAPES[args.shape]
@@ -53,7 +54,15 @@ def main():
     el, er = torch.randn(n, H, device=dev), torch.randn(n, H, device=dev)
     dZ = torch.randn(n, H, F, device=dev)
     gi.csc(), gi.csr()
-    res = {"shape": args.shape, "nodes": n, "edges": E, "H": H, "F": F}
+    res = {"shape": args.shape, "nodes": n, "edges": E, "H": H, "F": F, "degree": args.degree}
+    for thr in [int(x) for x in args.row_hub.split(",") if x]:
+        K.HUB_THRESHOLD = thr
+        rst, mx, sm, _ = K._gat_fwd(gi, ft, el, er, 0.2, 0.0, 0)
+        print(json.dumps({"row_hub": thr, "H": H, "F": F, "degree": args.degree, "shape": args.shape,
+                          "fused_fwd_ms": timeit(lambda: K._gat_fwd(gi, ft, el, er, 0.2, 0.0, 0), args.reps),
+                          "fused_bwd_ms": timeit(lambda: K._gat_bwd(gi, ft, el, er, mx, sm, dZ, 0.2, 0.0, 0), args.reps)}),
+              flush=True)
+    K.HUB_THRESHOLD = None
     rst, mx, sm, _ = K._gat_fwd(gi, ft, el, er, 0.2, 0.0, 0)
     res["fused_fwd_ms"] = timeit(lambda: K._gat_fwd(gi, ft, el, er, 0.2, 0.0, 0), args.reps)
     res["fused_bwd_ms"] = timeit(lambda: K._gat_bwd(gi, ft, el, er, mx, sm, dZ, 0.2, 0.0, 0), args.reps)

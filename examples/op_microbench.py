@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--order", default="shuffled")
     ap.add_argument("--softmax-heads", default="", help="comma list: also time edge_softmax fwd/bwd with H heads")
     ap.add_argument("--hub-bytes", type=int, default=0, help="override: hub threshold = hub_bytes / (4*D)")
+    ap.add_argument("--softmax-hub", default="", help="comma list of edge_softmax hub cut-offs (edges) to sweep; 0 = default")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     n, e, _, _ = synthetic.SHAPES[args.shape]
@@ -63,7 +64,8 @@ def main():
         print(json.dumps(res), flush=True)
     if args.softmax_heads:
         from dgl import sparse as K2
-        for H in [int(x) for x in args.softmax_heads.split(",")]:
+        for H, thr in [(int(x), int(y)) for x in args.softmax_heads.split(",") for y in (args.softmax_hub or "0").split(",")]:
+            K2.HUB_THRESHOLD = thr or None
             z = torch.randn(e, H, device=dev)
             a = K2._edge_softmax_fwd(g._graph, z)
             gr = torch.randn(e, H, device=dev)
@@ -71,7 +73,7 @@ def main():
             Bb = 4 * (n + 1) + 4 * p * e + 3 * 4 * H * e
             tf = timeit(lambda: K2._edge_softmax_fwd(g._graph, z))
             tb = timeit(lambda: K2._edge_softmax_bwd(g._graph, a, gr))
-            print(json.dumps({"shape": args.shape, "edges": e, "H": H, "order": args.order, "degree": args.degree,
+            print(json.dumps({"shape": args.shape, "edges": e, "H": H, "order": args.order, "degree": args.degree, "hub": thr,
                               "edge_softmax_fwd": {"ms": round(tf, 4), "gbs": round(Bf / tf / 1e6), "frac": round(Bf / tf / 1e6 / peak, 3)},
                               "edge_softmax_bwd": {"ms": round(tb, 4), "gbs": round(Bb / tb / 1e6), "frac": round(Bb / tb / 1e6 / peak, 3)}}),
                   flush=True)

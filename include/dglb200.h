@@ -110,8 +110,8 @@ int dglb_csr_find_hub_rows(int64_t n_rows, const int32_t* indptr, int32_t thresh
                            int32_t* hub_rows, int64_t cap, int32_t* n_hub, void* stream);
 /* thresholds the library recommends for a given feature width (elements): the first for the
  * segmented hub path of gspmm / gsddmm (64-256 edges: a row-task's duration follows its edge count),
- * the second for the one-CTA-per-hub-row path of the fused GAT kernels (only real hubs: ~1.5 MB of
- * gather per row-task, 256-8192 edges), the third for the segmented hub path of edge_softmax
+ * the second for the one-CTA-per-hub-row path of the fused GAT kernels (128 edges: measured optimum of
+ * a sweep on power-law graphs), the third for the segmented hub path of edge_softmax
  * (64-1024 edges by head count: one warp walks a segment in ~32 trips per pass) */
 int32_t dglb_default_hub_threshold(int64_t out_len);
 int32_t dglb_default_row_hub_threshold(int64_t out_len);
