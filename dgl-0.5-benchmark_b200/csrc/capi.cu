@@ -269,13 +269,14 @@ int dglb_edge_softmax_bwd(int dtype, int64_t n_dst, int64_t nnz, int64_t n_heads
 
 static void gat_zero(GatParams& p) { memset(&p, 0, sizeof(p)); }
 
+size_t dglb_gat_hub_workspace_bytes(int64_t n_seg, int64_t n_heads, int64_t head_dim) {
+  return gat_hub_workspace_bytes(n_seg, n_heads, head_dim);
+}
+
 int dglb_gat_fused_fwd(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz, int64_t n_heads, int64_t head_dim,
                        float negative_slope, float dropout_p, uint64_t seed, const int32_t* indptr,
                        const int32_t* indices, const int32_t* eids, const void* ft, const void* el, const void* er,
                        void* rst, float* row_max, float* row_sum, void* edge_scores, const dglb_hub_t* hub, void* stream) {
-  const int32_t* hub_rows = hub ? hub->rows : nullptr;
-  const int32_t n_hub = hub ? hub->n_hub : 0;
-  const int32_t hub_threshold = hub ? hub->threshold : 0;
   (void)n_src;
   if (dtype != DGLB_F32) { set_error("gat_fused: only f32 is implemented"); return DGLB_E_UNSUPPORTED; }
   DGLB_CHECK_ARG(n_dst >= 0 && nnz >= 0 && indptr && (indices || nnz == 0), "gat_fused_fwd: bad graph");
@@ -287,8 +288,8 @@ int dglb_gat_fused_fwd(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz, int
   p.ft = static_cast<const float*>(ft); p.el = static_cast<const float*>(el); p.er = static_cast<const float*>(er);
   p.out_feat = static_cast<float*>(rst); p.out_h0 = row_max; p.out_h1 = row_sum;
   p.row_max = row_max; p.row_sum = row_sum;
-  p.edge_scores = static_cast<float*>(edge_scores); p.hub_rows = hub_rows; p.n_rows = n_dst; p.slope = negative_slope;
-  return gat_fused_f32(0, p, n_heads, head_dim, dropout_p, seed, n_hub, hub_threshold, static_cast<cudaStream_t>(stream));
+  p.edge_scores = static_cast<float*>(edge_scores); p.n_rows = n_dst; p.slope = negative_slope;
+  return gat_fused_f32(0, p, n_heads, head_dim, dropout_p, seed, hub, static_cast<cudaStream_t>(stream));
 }
 
 int dglb_gat_fused_bwd_dst(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz, int64_t n_heads, int64_t head_dim,
@@ -296,9 +297,6 @@ int dglb_gat_fused_bwd_dst(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz,
                            const int32_t* indices, const int32_t* eids, const void* ft, const void* el,
                            const void* er, const float* row_max, const float* row_sum, const void* grad_rst,
                            float* row_pack, void* grad_er, const dglb_hub_t* hub, void* stream) {
-  const int32_t* hub_rows = hub ? hub->rows : nullptr;
-  const int32_t n_hub = hub ? hub->n_hub : 0;
-  const int32_t hub_threshold = hub ? hub->threshold : 0;
   (void)n_src;
   if (dtype != DGLB_F32) { set_error("gat_fused: only f32 is implemented"); return DGLB_E_UNSUPPORTED; }
   DGLB_CHECK_ARG(n_dst >= 0 && nnz >= 0 && indptr && (indices || nnz == 0), "gat_fused_bwd_dst: bad graph");
@@ -310,9 +308,9 @@ int dglb_gat_fused_bwd_dst(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz,
   p.indptr = indptr; p.indices = indices; p.eids = eids;
   p.ft = static_cast<const float*>(ft); p.el = static_cast<const float*>(el); p.er = static_cast<const float*>(er);
   p.row_max = row_max; p.row_sum = row_sum; p.dZ = static_cast<const float*>(grad_rst);
-  p.out_pack = reinterpret_cast<float4*>(row_pack); p.out_h0 = static_cast<float*>(grad_er); p.hub_rows = hub_rows;
+  p.out_pack = reinterpret_cast<float4*>(row_pack); p.out_h0 = static_cast<float*>(grad_er);
   p.n_rows = n_dst; p.slope = negative_slope;
-  return gat_fused_f32(1, p, n_heads, head_dim, dropout_p, seed, n_hub, hub_threshold, static_cast<cudaStream_t>(stream));
+  return gat_fused_f32(1, p, n_heads, head_dim, dropout_p, seed, hub, static_cast<cudaStream_t>(stream));
 }
 
 int dglb_gat_fused_bwd_src(int dtype, int64_t n_src, int64_t n_dst, int64_t nnz, int64_t n_heads, int64_t head_dim,
@@ -320,9 +318,6 @@ int dglb_gat_fused_bwd_src(int dtype, int64_t n_src, int64_t n_dst, int64_t nnz,
                            const int32_t* indices_csr, const int32_t* eids_csr, const void* ft, const void* el,
                            const float* row_pack, const void* grad_rst, void* grad_ft, void* grad_el,
                            const dglb_hub_t* hub, void* stream) {
-  const int32_t* hub_rows = hub ? hub->rows : nullptr;
-  const int32_t n_hub = hub ? hub->n_hub : 0;
-  const int32_t hub_threshold = hub ? hub->threshold : 0;
   (void)n_dst;
   if (dtype != DGLB_F32) { set_error("gat_fused: only f32 is implemented"); return DGLB_E_UNSUPPORTED; }
   DGLB_CHECK_ARG(n_src >= 0 && nnz >= 0 && indptr_csr && (indices_csr || nnz == 0), "gat_fused_bwd_src: bad graph");
@@ -334,9 +329,9 @@ int dglb_gat_fused_bwd_src(int dtype, int64_t n_src, int64_t n_dst, int64_t nnz,
   p.indptr = indptr_csr; p.indices = indices_csr; p.eids = eids_csr;
   p.ft = static_cast<const float*>(ft); p.el = static_cast<const float*>(el);
   p.pack = reinterpret_cast<const float4*>(row_pack); p.dZ = static_cast<const float*>(grad_rst);
-  p.out_feat = static_cast<float*>(grad_ft); p.out_h0 = static_cast<float*>(grad_el); p.hub_rows = hub_rows;
+  p.out_feat = static_cast<float*>(grad_ft); p.out_h0 = static_cast<float*>(grad_el);
   p.n_rows = n_src; p.slope = negative_slope;
-  return gat_fused_f32(2, p, n_heads, head_dim, dropout_p, seed, n_hub, hub_threshold, static_cast<cudaStream_t>(stream));
+  return gat_fused_f32(2, p, n_heads, head_dim, dropout_p, seed, hub, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

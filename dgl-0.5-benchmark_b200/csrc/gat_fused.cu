@@ -26,7 +26,13 @@
 //      S3 = sum_j a_j g_j comes from the owner lanes;  grad_er = S2 - S1*S3;  writes the 16-byte
 //      record row_pack[v,h] = {er, max, sum, S1}.
 //   src pass (CSR): grad_ft[u] = sum a*drop*dZ[v];  grad_el[u] = sum a g (dd - S1[v]).
-// Hub rows: one CTA per row; the groups split the edges and meet in shared memory.
+// Hub rows (more than hub_threshold edges), when the caller hands over the segment lists and a workspace
+//   (dglb_hub_t): every SEGMENT of <= seg_len edges is processed by a group exactly like an ordinary row
+//   (same kernels, MODE = GAT_SEG) and writes PARTIAL results -- all three passes are linear in the edges once
+//   the row's max / sum are known -- which small combine kernels fold in segment order (deterministic).
+//   The forward statistics of hub rows come from two small kernels first (per-segment max / sum, rescaled
+//   and combined per row).  Without a workspace: one CTA per hub row (MODE = GAT_HUB_CTA), the groups split
+//   the edges and meet in shared memory.
 #include <cstdlib>
 
 #include "kernels.cuh"
@@ -34,6 +40,8 @@
 namespace dglb {
 
 constexpr int kMaxHeads = 8;
+
+enum : int { GAT_ROWS = 0, GAT_HUB_CTA = 1, GAT_SEG = 2 };
 
 // counter-based dropout: keep iff hash(seed, edge*H + h) maps to u >= p
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
@@ -74,13 +82,14 @@ __device__ __forceinline__ void cta_allreduce_sum(float (&v)[HT], float* s_buf, 
   }
 }
 
-// row / slice of the calling group (same scheme as spmm.cu / sddmm.cu)
-template <bool HUB>
+// row / slice / segment of the calling group (same scheme as spmm.cu / sddmm.cu)
+template <int MODE>
 __device__ __forceinline__ void gat_group_work(const GatParams& p, int64_t& row, bool& active, int64_t& j0,
-                                               int& n, int& gidx, int& n_groups) {
+                                               int& n, int& gidx, int& n_groups, int& seg) {
   n_groups = kBlockThreads >> p.log2G;
   gidx = threadIdx.x >> p.log2G;
-  if constexpr (!HUB) {
+  seg = 0;
+  if constexpr (MODE == GAT_ROWS) {
     row = ((int64_t)blockIdx.x * kBlockThreads + threadIdx.x) >> p.log2G;
     active = row < p.n_rows;
     j0 = 0; n = 0;
@@ -91,6 +100,19 @@ __device__ __forceinline__ void gat_group_work(const GatParams& p, int64_t& row,
       else { j0 = s; n = d; }
     }
     if (!active) row = 0;
+  } else if constexpr (MODE == GAT_SEG) {
+    const int64_t sg = ((int64_t)blockIdx.x * kBlockThreads + threadIdx.x) >> p.log2G;
+    active = sg < p.n_seg;
+    row = 0; j0 = 0; n = 0;
+    if (active) {
+      seg = (int)sg;
+      const int hub = __ldg(p.seg_hub + seg);
+      row = __ldg(p.hub_rows + hub);
+      const int k = seg - __ldg(p.seg_ptr + hub);
+      const int s = __ldg(p.indptr + row) + k * p.seg_len;
+      j0 = s;
+      n = min(p.seg_len, __ldg(p.indptr + row + 1) - s);
+    }
   } else {
     row = p.hub_rows[blockIdx.x];
     active = true;
@@ -131,12 +153,13 @@ __device__ __forceinline__ void cta_allreduce_max(float (&v)[HT], float* s_buf, 
 template <int HT, int NW>
 __device__ __forceinline__ int group_stride(int G) { return (G * HT + (G >= 8 ? HT : 0)) * NW; }
 
-// shared epilogue: write a feature tile (row kernel) or combine the CTA's groups (hub kernel)
-template <int VEC, int CH, bool HUB>
+// shared epilogue: write a feature tile to `out_row` (the row of the output, or the segment's row of the
+// workspace) or combine the CTA's groups (CTA-per-hub-row kernel)
+template <int VEC, int CH, int MODE>
 __device__ __forceinline__ void store_feat_tile(const GatParams& p, float (&acc)[CH][VEC], const bool (&colv)[CH],
-                                                const int (&k)[CH], int64_t row, bool active, int tile0, int lg,
-                                                int gidx, int n_groups, float* s_val) {
-  if constexpr (!HUB) {
+                                                const int (&k)[CH], float* out_row, int64_t row, bool active,
+                                                int tile0, int lg, int gidx, int n_groups, float* s_val) {
+  if constexpr (MODE != GAT_HUB_CTA) {
     if (active) {
 #pragma unroll
       for (int c = 0; c < CH; ++c)
@@ -144,7 +167,7 @@ __device__ __forceinline__ void store_feat_tile(const GatParams& p, float (&acc)
           FVec<VEC> o;
 #pragma unroll
           for (int v = 0; v < VEC; ++v) o.v[v] = acc[c][v];
-          st_vec<VEC>(p.out_feat + row * (int64_t)p.D + k[c], o);
+          st_vec<VEC>(out_row + k[c], o);
         }
     }
   } else {
@@ -168,9 +191,11 @@ __device__ __forceinline__ void store_feat_tile(const GatParams& p, float (&acc)
 }
 
 // ------------------------------------------------------------------ forward
-template <int VEC, int CH, int HT, int UT, bool HUB>
+template <int VEC, int CH, int HT, int UT, int MODE>
 __global__ void __launch_bounds__(kBlockThreads, UT == 4 ? 3 : 2) gat_fwd_kernel(const GatParams p) {
   constexpr int U = UT / CH > 0 ? UT / CH : 1;
+  constexpr bool HUB = MODE == GAT_HUB_CTA;
+  constexpr bool SEG = MODE == GAT_SEG;
   __shared__ __align__(16) float s_w[(kBlockThreads + 32) * HT];  // [group][edge slot][head] weights
   extern __shared__ __align__(16) unsigned char smem_raw[];       // hub rows only
   float* s_buf = reinterpret_cast<float*>(smem_raw);
@@ -178,12 +203,14 @@ __global__ void __launch_bounds__(kBlockThreads, UT == 4 ? 3 : 2) gat_fwd_kernel
   const int lg = threadIdx.x & (G - 1);
   int64_t row, j0;
   bool active;
-  int n, gidx, n_groups;
-  gat_group_work<HUB>(p, row, active, j0, n, gidx, n_groups);
+  int n, gidx, n_groups, seg;
+  gat_group_work<MODE>(p, row, active, j0, n, gidx, n_groups, seg);
   const int nmax = __reduce_max_sync(FULL_MASK, n);
-  const bool single = nmax <= G;  // every row of this warp fits one batch: logits stay in registers
+  const bool single = !SEG && nmax <= G;  // every row of this warp fits one batch: logits stay in registers
   const bool live = active || HUB;
   const bool need_e = p.drop_p > 0.f || p.edge_scores != nullptr;
+  const bool prefetch = !SEG && p.prefetch;
+  float* out_row = SEG ? p.ws_feat + (int64_t)seg * p.D : p.out_feat + row * (int64_t)p.D;
   float* my_w = s_w + gidx * group_stride<HT, 1>(G);
 
   float er_h[HT], mx[HT], sm[HT], e_reg[HT];
@@ -197,11 +224,19 @@ __global__ void __launch_bounds__(kBlockThreads, UT == 4 ? 3 : 2) gat_fwd_kernel
   // overlaps the idx -> el -> reduce chain below
   FVec<VEC> xv[U][CH];
   const int m_first = min(n, G);
+  if constexpr (SEG) {
+    // segment of a hub row: the row's statistics were combined from the per-segment ones beforehand
+    if (active) {
+#pragma unroll
+      for (int h = 0; h < HT; ++h)
+        if (h < H) { mx[h] = __ldg(p.row_max + row * H + h); sm[h] = __ldg(p.row_sum + row * H + h); }
+    }
+  } else {
   // ---- statistics 1: per-head max of the logits
   for (int off = 0; off < nmax; off += G) {
     const bool valid = off + lg < n;
     const int c = valid ? __ldg(p.indices + j0 + off + lg) : 0;
-    if (off == 0 && p.prefetch) {
+    if (off == 0 && prefetch) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int cu = __shfl_sync(FULL_MASK, c, u, G);
@@ -239,10 +274,12 @@ __global__ void __launch_bounds__(kBlockThreads, UT == 4 ? 3 : 2) gat_fwd_kernel
   }
   group_allreduce_sum<HT>(sm, G);
   if constexpr (HUB) cta_allreduce_sum<HT>(sm, s_buf, gidx, lg, n_groups);
-  if (active && lg < H && (!HUB || gidx == 0)) {
+  if (!SEG && active && lg < H && (!HUB || gidx == 0)) {
 #pragma unroll
     for (int h = 0; h < HT; ++h)
       if (h == lg) { p.out_h0[row * H + h] = mx[h]; p.out_h1[row * H + h] = sm[h]; }
+  }
+
   }
 
   // ---- weighted gather of the source rows
@@ -282,7 +319,7 @@ __global__ void __launch_bounds__(kBlockThreads, UT == 4 ? 3 : 2) gat_fwd_kernel
       __syncwarp();
       const int mmax = min(G, nmax - off);
       int t_begin = 0;
-      if (tile0 == 0 && off == 0 && p.prefetch) {
+      if (tile0 == 0 && off == 0 && prefetch) {
         // first batch of the row: its source rows were requested before the statistics
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -325,7 +362,7 @@ __global__ void __launch_bounds__(kBlockThreads, UT == 4 ? 3 : 2) gat_fwd_kernel
       }
       __syncwarp();  // the next batch overwrites the weight slots
     }
-    store_feat_tile<VEC, CH, HUB>(p, acc, colv, k, row, active, tile0, lg, gidx, n_groups, s_buf + n_groups * HT);
+    store_feat_tile<VEC, CH, MODE>(p, acc, colv, k, out_row, row, active, tile0, lg, gidx, n_groups, s_buf + n_groups * HT);
   }
 }
 
@@ -334,9 +371,11 @@ __global__ void __launch_bounds__(kBlockThreads, UT == 4 ? 3 : 2) gat_fwd_kernel
 //            outputs row_pack[v,h] = {er, max, sum, S1}, grad_er[v,h].
 // SRC_PASS = true : CSR over src rows u.  neighbour = dst v: gathers dZ[v] (owner: row_pack[v,:]); own row: ft[u].
 //            outputs grad_ft[u,:], grad_el[u,h].
-template <int VEC, int CH, int HT, int UT, bool SRC_PASS, bool HUB>
+template <int VEC, int CH, int HT, int UT, bool SRC_PASS, int MODE>
 __global__ void __launch_bounds__(kBlockThreads, UT == 4 ? 3 : 2) gat_bwd_kernel(const GatParams p) {
   constexpr int U = UT / CH > 0 ? UT / CH : 1;
+  constexpr bool HUB = MODE == GAT_HUB_CTA;
+  constexpr bool SEG = MODE == GAT_SEG;
   __shared__ __align__(16) float s_w[(kBlockThreads + 32) * HT * 2];  // [group][edge slot][head]{a*drop, a*drop*g}
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* s_buf = reinterpret_cast<float*>(smem_raw);
@@ -344,11 +383,12 @@ __global__ void __launch_bounds__(kBlockThreads, UT == 4 ? 3 : 2) gat_bwd_kernel
   const int lg = threadIdx.x & (G - 1);
   int64_t row, j0;
   bool active;
-  int n, gidx, n_groups;
-  gat_group_work<HUB>(p, row, active, j0, n, gidx, n_groups);
+  int n, gidx, n_groups, seg;
+  gat_group_work<MODE>(p, row, active, j0, n, gidx, n_groups, seg);
   const int nmax = __reduce_max_sync(FULL_MASK, n);
   const bool live = active || HUB;
   const bool need_e = p.drop_p > 0.f;
+  float* out_row = SEG ? p.ws_feat + (int64_t)seg * p.D : p.out_feat + row * (int64_t)p.D;
   float2* my_w = reinterpret_cast<float2*>(s_w + gidx * group_stride<HT, 2>(G));
 
   const float* __restrict__ own_feat = (SRC_PASS ? p.ft : p.dZ) + row * (int64_t)p.D;
@@ -460,7 +500,7 @@ __global__ void __launch_bounds__(kBlockThreads, UT == 4 ? 3 : 2) gat_bwd_kernel
       for (int h = 0; h < HT; ++h)
         if (colv[c] && hk[c] == h) { tot1[h] += p1[c]; tot2[h] += p2[c]; }
     if constexpr (SRC_PASS) {
-      store_feat_tile<VEC, CH, HUB>(p, acc, colv, k, row, active, tile0, lg, gidx, n_groups, s_buf + n_groups * HT);
+      store_feat_tile<VEC, CH, MODE>(p, acc, colv, k, out_row, row, active, tile0, lg, gidx, n_groups, s_buf + n_groups * HT);
     }
   }
   // ---- once-per-row reductions
@@ -471,6 +511,18 @@ __global__ void __launch_bounds__(kBlockThreads, UT == 4 ? 3 : 2) gat_bwd_kernel
     cta_allreduce_sum<HT>(tot1, s_buf, gidx, lg, n_groups);
     cta_allreduce_sum<HT>(tot2, s_buf, gidx, lg, n_groups);
     cta_allreduce_sum<HT>(tot3, s_buf, gidx, lg, n_groups);
+  }
+  if constexpr (SEG) {
+    // partial sums of this segment; gat_seg_tot_combine_kernel folds a row's segments in order
+    if (active && lg < H) {
+#pragma unroll
+      for (int h = 0; h < HT; ++h)
+        if (h == lg) {
+          float* w = p.ws_tot + ((int64_t)seg * H + h) * 4;
+          w[0] = tot1[h]; w[1] = tot2[h]; w[2] = tot3[h];
+        }
+    }
+    return;
   }
   if (active && lg < H && (!HUB || gidx == 0)) {
 #pragma unroll
@@ -485,6 +537,95 @@ __global__ void __launch_bounds__(kBlockThreads, UT == 4 ? 3 : 2) gat_bwd_kernel
       }
   }
 }
+
+// ------------------------------------------------------------------ hub rows by segments: small kernels
+// forward statistics of one segment: a warp per segment, lanes = (edge slot, head) as in edge_softmax.cu;
+// ws_tot[seg, h] = {max_s, sum_s = sum exp(e - max_s)}
+__global__ void __launch_bounds__(kBlockThreads) gat_seg_stats_kernel(const GatParams p) {
+  const int lane = threadIdx.x & 31;
+  const int seg = (int)(((int64_t)blockIdx.x * kBlockThreads + threadIdx.x) >> 5);
+  if (seg >= p.n_seg) return;
+  const int H = p.H;
+  const int h = lane & (p.HP - 1);
+  const bool hv = h < H;
+  const int slot = lane >> p.log2HP, nslots = 32 >> p.log2HP;
+  const int hub = __ldg(p.seg_hub + seg);
+  const int64_t row = __ldg(p.hub_rows + hub);
+  const int begin = __ldg(p.indptr + row) + (seg - __ldg(p.seg_ptr + hub)) * p.seg_len;
+  const int n = min(p.seg_len, __ldg(p.indptr + row + 1) - begin);
+  const float er = hv ? __ldg(p.er + row * H + h) : 0.f;
+  float mx = -INFINITY;
+#pragma unroll 4
+  for (int i = slot; i < n; i += nslots) {
+    const int c = __ldg(p.indices + begin + i);
+    if (hv) mx = fmaxf(mx, lrelu(__fadd_rn(__ldg(p.el + (int64_t)c * H + h), er), p.slope));
+  }
+  for (int s = 16; s >= p.HP; s >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, s));
+  float sum = 0.f;
+#pragma unroll 4
+  for (int i = slot; i < n; i += nslots) {
+    const int c = __ldg(p.indices + begin + i);
+    if (hv) sum += expf(__fsub_rn(lrelu(__fadd_rn(__ldg(p.el + (int64_t)c * H + h), er), p.slope), mx));
+  }
+  for (int s = 16; s >= p.HP; s >>= 1) sum += __shfl_xor_sync(FULL_MASK, sum, s);
+  if (slot == 0 && hv) {
+    float* w = p.ws_tot + ((int64_t)seg * H + h) * 4;
+    w[0] = mx; w[1] = sum;
+  }
+}
+
+// per hub row and head: max = max_s max_s, sum = sum_s sum_s * exp(max_s - max), segment order
+__global__ void __launch_bounds__(kBlockThreads) gat_seg_stats_combine_kernel(const GatParams p) {
+  const int64_t idx = (int64_t)blockIdx.x * kBlockThreads + threadIdx.x;
+  if (idx >= (int64_t)p.n_hub * p.H) return;
+  const int hub = (int)(idx / p.H), h = (int)(idx - (int64_t)hub * p.H);
+  const int s0 = __ldg(p.seg_ptr + hub), s1 = __ldg(p.seg_ptr + hub + 1);
+  const int64_t row = __ldg(p.hub_rows + hub);
+  float mx = -INFINITY;
+  for (int sg = s0; sg < s1; ++sg) mx = fmaxf(mx, p.ws_tot[((int64_t)sg * p.H + h) * 4]);
+  float sum = 0.f;
+  for (int sg = s0; sg < s1; ++sg) {
+    const float* w = p.ws_tot + ((int64_t)sg * p.H + h) * 4;
+    sum += w[1] * expf(__fsub_rn(w[0], mx));
+  }
+  p.out_h0[row * p.H + h] = mx;
+  p.out_h1[row * p.H + h] = sum;
+}
+
+// out_feat[row, k] = sum over the row's segments of ws_feat[seg, k], segment order
+__global__ void __launch_bounds__(kBlockThreads) gat_seg_feat_combine_kernel(const GatParams p) {
+  const int64_t idx = (int64_t)blockIdx.x * kBlockThreads + threadIdx.x;
+  if (idx >= (int64_t)p.n_hub * p.D) return;
+  const int hub = (int)(idx / p.D), k = (int)(idx - (int64_t)hub * p.D);
+  const int s0 = __ldg(p.seg_ptr + hub), s1 = __ldg(p.seg_ptr + hub + 1);
+  float a = p.ws_feat[(int64_t)s0 * p.D + k];
+  for (int sg = s0 + 1; sg < s1; ++sg) a = __fadd_rn(a, p.ws_feat[(int64_t)sg * p.D + k]);
+  p.out_feat[(int64_t)__ldg(p.hub_rows + hub) * p.D + k] = a;
+}
+
+// backward totals of a hub row from its segments' partials (same closing formulas as gat_bwd_kernel)
+template <bool SRC_PASS>
+__global__ void __launch_bounds__(kBlockThreads) gat_seg_tot_combine_kernel(const GatParams p) {
+  const int64_t idx = (int64_t)blockIdx.x * kBlockThreads + threadIdx.x;
+  if (idx >= (int64_t)p.n_hub * p.H) return;
+  const int hub = (int)(idx / p.H), h = (int)(idx - (int64_t)hub * p.H);
+  const int s0 = __ldg(p.seg_ptr + hub), s1 = __ldg(p.seg_ptr + hub + 1);
+  const int64_t row = __ldg(p.hub_rows + hub);
+  float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  for (int sg = s0; sg < s1; ++sg) {
+    const float* w = p.ws_tot + ((int64_t)sg * p.H + h) * 4;
+    t1 += w[0]; t2 += w[1]; t3 += w[2];
+  }
+  if constexpr (!SRC_PASS) {
+    p.out_pack[row * p.H + h] = make_float4(__ldg(p.er + row * p.H + h), __ldg(p.row_max + row * p.H + h),
+                                            __ldg(p.row_sum + row * p.H + h), t1);
+    p.out_h0[row * p.H + h] = __fsub_rn(t2, t1 * t3);
+  } else {
+    p.out_h0[row * p.H + h] = __fsub_rn(t2, t3);
+  }
+}
+
+static unsigned blocks_for(int64_t items) { return (unsigned)((items + kBlockThreads - 1) / kBlockThreads); }
 
 // ------------------------------------------------------------------ dispatch
 static int gat_geometry(GatParams& p, int64_t H, int64_t F, const void* a0, const void* a1, const void* a2,
@@ -528,10 +669,20 @@ template <int VEC, int CH, int HT, int UT>
 static int launch_gat_fwd_ut(const GatParams& p, int n_hub, cudaStream_t stream) {
   const int rows_per_block = kBlockThreads / p.G;
   const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
-  gat_fwd_kernel<VEC, CH, HT, UT, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+  gat_fwd_kernel<VEC, CH, HT, UT, GAT_ROWS><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
   DGLB_LAUNCH_CHECK("gat_fwd_kernel");
-  if (n_hub > 0) {
-    gat_fwd_kernel<VEC, CH, HT, UT, true><<<n_hub, kBlockThreads, gat_hub_smem(p, VEC, CH, HT), stream>>>(p);
+  if (n_hub > 0 && p.n_seg > 0) {
+    gat_seg_stats_kernel<<<blocks_for((int64_t)p.n_seg * 32), kBlockThreads, 0, stream>>>(p);
+    DGLB_LAUNCH_CHECK("gat_seg_stats_kernel");
+    gat_seg_stats_combine_kernel<<<blocks_for((int64_t)p.n_hub * p.H), kBlockThreads, 0, stream>>>(p);
+    DGLB_LAUNCH_CHECK("gat_seg_stats_combine_kernel");
+    const int64_t sblocks = (p.n_seg + rows_per_block - 1) / rows_per_block;
+    gat_fwd_kernel<VEC, CH, HT, UT, GAT_SEG><<<(unsigned)sblocks, kBlockThreads, 0, stream>>>(p);
+    DGLB_LAUNCH_CHECK("gat_fwd_kernel(seg)");
+    gat_seg_feat_combine_kernel<<<blocks_for((int64_t)p.n_hub * p.D), kBlockThreads, 0, stream>>>(p);
+    DGLB_LAUNCH_CHECK("gat_seg_feat_combine_kernel");
+  } else if (n_hub > 0) {
+    gat_fwd_kernel<VEC, CH, HT, UT, GAT_HUB_CTA><<<n_hub, kBlockThreads, gat_hub_smem(p, VEC, CH, HT), stream>>>(p);
     DGLB_LAUNCH_CHECK("gat_fwd_kernel(hub)");
   }
   return DGLB_OK;
@@ -548,12 +699,26 @@ static int launch_gat_bwd_ut(int which, const GatParams& p, int n_hub, cudaStrea
   const int rows_per_block = kBlockThreads / p.G;
   const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
   const size_t smem = gat_hub_smem(p, VEC, CH, HT);
-  if (which == 1) gat_bwd_kernel<VEC, CH, HT, UT, false, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
-  else gat_bwd_kernel<VEC, CH, HT, UT, true, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+  if (which == 1) gat_bwd_kernel<VEC, CH, HT, UT, false, GAT_ROWS><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+  else gat_bwd_kernel<VEC, CH, HT, UT, true, GAT_ROWS><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
   DGLB_LAUNCH_CHECK("gat_bwd_kernel");
-  if (n_hub > 0) {
-    if (which == 1) gat_bwd_kernel<VEC, CH, HT, UT, false, true><<<n_hub, kBlockThreads, smem, stream>>>(p);
-    else gat_bwd_kernel<VEC, CH, HT, UT, true, true><<<n_hub, kBlockThreads, smem, stream>>>(p);
+  if (n_hub > 0 && p.n_seg > 0) {
+    const int64_t sblocks = (p.n_seg + rows_per_block - 1) / rows_per_block;
+    if (which == 1) {
+      gat_bwd_kernel<VEC, CH, HT, UT, false, GAT_SEG><<<(unsigned)sblocks, kBlockThreads, 0, stream>>>(p);
+      DGLB_LAUNCH_CHECK("gat_bwd_kernel(seg)");
+      gat_seg_tot_combine_kernel<false><<<blocks_for((int64_t)p.n_hub * p.H), kBlockThreads, 0, stream>>>(p);
+    } else {
+      gat_bwd_kernel<VEC, CH, HT, UT, true, GAT_SEG><<<(unsigned)sblocks, kBlockThreads, 0, stream>>>(p);
+      DGLB_LAUNCH_CHECK("gat_bwd_kernel(seg)");
+      gat_seg_feat_combine_kernel<<<blocks_for((int64_t)p.n_hub * p.D), kBlockThreads, 0, stream>>>(p);
+      DGLB_LAUNCH_CHECK("gat_seg_feat_combine_kernel");
+      gat_seg_tot_combine_kernel<true><<<blocks_for((int64_t)p.n_hub * p.H), kBlockThreads, 0, stream>>>(p);
+    }
+    DGLB_LAUNCH_CHECK("gat_seg_tot_combine_kernel");
+  } else if (n_hub > 0) {
+    if (which == 1) gat_bwd_kernel<VEC, CH, HT, UT, false, GAT_HUB_CTA><<<n_hub, kBlockThreads, smem, stream>>>(p);
+    else gat_bwd_kernel<VEC, CH, HT, UT, true, GAT_HUB_CTA><<<n_hub, kBlockThreads, smem, stream>>>(p);
     DGLB_LAUNCH_CHECK("gat_bwd_kernel(hub)");
   }
   return DGLB_OK;
@@ -583,9 +748,13 @@ static int dispatch_gat(int which, const GatParams& p, int ht, int n_hub, cudaSt
   }
 }
 
+size_t gat_hub_workspace_bytes(int64_t n_seg, int64_t H, int64_t F) {
+  return (size_t)n_seg * (size_t)(H * F + 4 * H) * sizeof(float);
+}
+
 // which: 0 fwd, 1 bwd_dst, 2 bwd_src
 int gat_fused_f32(int which, GatParams& p, int64_t H, int64_t F, float dropout_p, uint64_t seed,
-                  int32_t n_hub, int32_t hub_threshold, cudaStream_t stream) {
+                  const dglb_hub_t* hub, cudaStream_t stream) {
   if (p.n_rows == 0) return DGLB_OK;
   int vec, ch, ht;
   const void* a1 = which == 0 ? (const void*)p.out_feat : (const void*)p.dZ;
@@ -594,9 +763,24 @@ int gat_fused_f32(int which, GatParams& p, int64_t H, int64_t F, float dropout_p
     set_error("gat_fused: unsupported shape H=%lld F=%lld (need 1<=H<=8)", (long long)H, (long long)F);
     return DGLB_E_UNSUPPORTED;
   }
-  const bool hub = n_hub > 0 && p.hub_rows;
-  p.hub_threshold = hub ? hub_threshold : INT32_MAX;
-  if (!hub) n_hub = 0;
+  const bool use_hub = hub && hub->n_hub > 0 && hub->rows;
+  int n_hub = use_hub ? hub->n_hub : 0;
+  p.hub_rows = use_hub ? hub->rows : nullptr;
+  p.hub_threshold = use_hub ? hub->threshold : INT32_MAX;
+  p.n_hub = n_hub; p.n_seg = 0; p.seg_len = 0;
+  p.seg_ptr = nullptr; p.seg_hub = nullptr; p.ws_feat = nullptr; p.ws_tot = nullptr;
+  // segmented hub path when the caller provides the segment lists and a workspace; otherwise one CTA per hub row
+  if (use_hub && hub->seg_ptr && hub->seg_hub && hub->n_seg > 0 && hub->seg_len > 0 && hub->workspace) {
+    const size_t need = gat_hub_workspace_bytes(hub->n_seg, H, F);
+    if (hub->workspace_bytes < need) {
+      set_error("gat_fused: hub workspace too small (%zu < %zu bytes)", hub->workspace_bytes, need);
+      return DGLB_E_WORKSPACE;
+    }
+    DGLB_CHECK_ARG((reinterpret_cast<uintptr_t>(hub->workspace) & 15) == 0, "gat_fused: hub workspace must be 16-byte aligned");
+    p.seg_ptr = hub->seg_ptr; p.seg_hub = hub->seg_hub; p.n_seg = hub->n_seg; p.seg_len = hub->seg_len;
+    p.ws_feat = static_cast<float*>(hub->workspace);
+    p.ws_tot = p.ws_feat + (size_t)hub->n_seg * (size_t)(H * F);
+  }
   if (!(dropout_p >= 0.f && dropout_p < 1.f)) { set_error("gat_fused: dropout_p must be in [0,1)"); return DGLB_E_INVALID; }
   p.drop_p = dropout_p;
   p.drop_scale = 1.f / (1.f - dropout_p);

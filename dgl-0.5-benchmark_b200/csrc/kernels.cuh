@@ -38,6 +38,11 @@ struct GatParams {
   float4* __restrict__ out_pack;        // bwd_dst: (n_dst, H) {er, max, sum, s1}
   float* __restrict__ edge_scores;      // fwd only, may be null
   const int32_t* __restrict__ hub_rows;
+  const int32_t* __restrict__ seg_ptr;  // [n_hub+1] segmented hub path (null: one CTA per hub row)
+  const int32_t* __restrict__ seg_hub;  // [n_seg]
+  float* __restrict__ ws_feat;          // [n_seg][D]    per-segment partial feature rows
+  float* __restrict__ ws_tot;           // [n_seg][H][4] per-segment {max,sum} (fwd) / {S1,S2,S3} partials (bwd)
+  int seg_len, n_seg, n_hub;
   int64_t n_rows;
   int H, F, D;  // D = H*F
   int ncols;    // D / VEC
@@ -78,6 +83,7 @@ int edge_softmax_f32(bool bwd, int64_t n_dst, int64_t nnz, int64_t n_heads, cons
 size_t edge_softmax_workspace_bytes(int64_t n_seg, int64_t n_hub, int64_t n_heads);
 // gat_fused.cu  (which: 0 fwd, 1 bwd_dst, 2 bwd_src)
 int gat_fused_f32(int which, GatParams& p, int64_t H, int64_t F, float dropout_p, uint64_t seed,
-                  int32_t n_hub, int32_t hub_threshold, cudaStream_t stream);
+                  const dglb_hub_t* hub, cudaStream_t stream);
+size_t gat_hub_workspace_bytes(int64_t n_seg, int64_t H, int64_t F);
 
 }  // namespace dglb

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "dglb_default_row_hub_threshold": (_i32, [_i64]),
     "dglb_default_softmax_hub_threshold": (_i32, [_i64]),
     "dglb_edge_softmax_workspace_bytes": (ctypes.c_size_t, [_i64, _i64, _i64]),
+    "dglb_gat_hub_workspace_bytes": (ctypes.c_size_t, [_i64, _i64, _i64]),
     "dglb_hub_workspace_bytes": (ctypes.c_size_t, [_i64, _i64, _int]),
     "dglb_gspmm_csr": (_int, [_int, _int, _int, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _shape_t,
                               _shape_t, _vp, _vp, _vp, _vp, _int, _hub_t, _vp]),

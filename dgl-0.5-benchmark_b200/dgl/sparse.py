@@ -319,6 +319,23 @@ def _edge_softmax_bwd(gidx, out, grad_out):
     return grad
 
 
+GAT_HUB_SEGMENTS = True  # False: one CTA per hub row (the pre-segmentation path, kept for comparison)
+
+
+def _gat_hub_arg(view, H, F, dev, launches):
+    """Hub rows of a CSRView for the fused GAT kernels: segment lists + workspace (segmented path)."""
+    info = view.hubs(_hub_threshold(H * F, row_cta=True))
+    if info is None:
+        return None, None, 0
+    if not GAT_HUB_SEGMENTS:
+        st = info.struct(None)
+        return ctypes.byref(st), (st, None), 1
+    nbytes = _capi.lib().dglb_gat_hub_workspace_bytes(info.n_seg, int(H), int(F))
+    ws = torch.empty(max(4, nbytes // 4), dtype=torch.float32, device=dev)
+    st = info.struct(ws)
+    return ctypes.byref(st), (st, ws), launches
+
+
 def _gat_fwd(gidx, ft, el, er, slope, dropout_p, seed, want_scores=False, eids=None):
     """Fused GAT attention forward.  ft (n_src,H,F), el (n_src,H), er (n_dst,H) ->
     rst (n_dst,H,F), row_max, row_sum (n_dst,H) [, scores (E,H)].  `eids` (int32, CSC order) overrides
@@ -336,8 +353,7 @@ def _gat_fwd(gidx, ft, el, er, slope, dropout_p, seed, want_scores=False, eids=N
         return rst, row_max, row_sum, scores
     csc = gidx.csc()
     l = _capi.lib()
-    thr = _hub_threshold(H * F, row_cta=True)
-    hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
+    hub, _keep, hub_launches = _gat_hub_arg(csc, H, F, dev, 4)
     stream = _capi.enter(dev)
     rc = l.dglb_gat_fused_fwd(_capi.F32, csc.n_rows, csc.n_cols, csc.nnz, H, F, float(slope), float(dropout_p),
                               int(seed), _capi.ptr(csc.indptr), _capi.ptr(csc.indices),
@@ -358,8 +374,7 @@ def _gat_bwd_dst(gidx, ft, el, er, row_max, row_sum, grad_rst, slope, dropout_p,
     grad_er = torch.empty((gidx.n_dst, H), dtype=ft.dtype, device=dev)
     if gidx.n_dst:
         csc = gidx.csc()
-        thr = _hub_threshold(H * F, row_cta=True)
-        hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
+        hub, _keep, hub_launches = _gat_hub_arg(csc, H, F, dev, 2)
         stream = _capi.enter(dev)
         rc = _capi.lib().dglb_gat_fused_bwd_dst(
             _capi.F32, csc.n_rows, csc.n_cols, csc.nnz, H, F, float(slope), float(dropout_p), int(seed),
@@ -381,8 +396,7 @@ def _gat_bwd_src(csr, ft, el, row_pack, grad_rst, slope, dropout_p, seed, eids=N
     grad_ft = torch.empty_like(ft)
     grad_el = torch.empty((csr.n_rows, H), dtype=ft.dtype, device=dev)
     if csr.n_rows:
-        thr = _hub_threshold(H * F, row_cta=True)
-        hub, _keep, hub_launches = _hub_arg(csr.hubs(thr))
+        hub, _keep, hub_launches = _gat_hub_arg(csr, H, F, dev, 3)
         stream = _capi.enter(dev)
         rc = _capi.lib().dglb_gat_fused_bwd_src(
             _capi.F32, csr.n_rows, csr.n_cols, csr.nnz, H, F, float(slope), float(dropout_p), int(seed),

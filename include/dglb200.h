@@ -110,8 +110,8 @@ int dglb_csr_find_hub_rows(int64_t n_rows, const int32_t* indptr, int32_t thresh
                            int32_t* hub_rows, int64_t cap, int32_t* n_hub, void* stream);
 /* thresholds the library recommends for a given feature width (elements): the first for the
  * segmented hub path of gspmm / gsddmm (64-256 edges: a row-task's duration follows its edge count),
- * the second for the one-CTA-per-hub-row path of the fused GAT kernels (128 edges: measured optimum of
- * a sweep on power-law graphs), the third for the segmented hub path of edge_softmax
+ * the second for the hub path of the fused GAT kernels (128 edges: measured optimum of a sweep on
+ * power-law graphs), the third for the segmented hub path of edge_softmax
  * (64-1024 edges by head count: one warp walks a segment in ~32 trips per pass) */
 int32_t dglb_default_hub_threshold(int64_t out_len);
 int32_t dglb_default_row_hub_threshold(int64_t out_len);
@@ -124,7 +124,8 @@ int32_t dglb_default_softmax_hub_threshold(int64_t n_heads);
  * combines the segments of a row in segment order (deterministic, no atomics; max/min ties still
  * resolve to the first CSR entry).  edge_softmax uses the same segments (a warp per segment, three
  * launches: segment stats, per-row combine, apply; workspace dglb_edge_softmax_workspace_bytes).
- * The fused GAT kernels use one CTA per hub row.
+ * The fused GAT kernels process every segment like an ordinary row and combine the partial results
+ * (workspace dglb_gat_hub_workspace_bytes); without a workspace they use one CTA per hub row.
  *   rows     [n_hub]    hub row ids
  *   seg_ptr  [n_hub+1]  first segment of each hub row (prefix sum of ceil(nnz/seg_len))
  *   seg_hub  [n_seg]    index into rows[] of the hub row a segment belongs to
@@ -247,7 +248,12 @@ int dglb_edge_softmax_bwd(int dtype, int64_t n_dst, int64_t nnz, int64_t n_heads
  *                            grad_el[u,h]   = sum_{u->v} a*(dd - s1[v,h])*lrelu'
  * optional `edge_scores` (E,H) in edge-id order receives a_j (before dropout); pass NULL on the
  * training path.  n_heads <= 8.  hub lists refer to the matrix each kernel traverses.
+ * Hub rows: with the segment lists and hub->workspace >= dglb_gat_hub_workspace_bytes(n_seg, n_heads,
+ * head_dim) (16-byte aligned) every segment of a hub row is processed like an ordinary row and small
+ * combine kernels fold the partial results in segment order (all three passes are linear in the edges
+ * once the row's max / sum are known); without a workspace one CTA handles each hub row.
  */
+size_t dglb_gat_hub_workspace_bytes(int64_t n_seg, int64_t n_heads, int64_t head_dim);
 int dglb_gat_fused_fwd(int dtype, int64_t n_dst, int64_t n_src, int64_t nnz,
                        int64_t n_heads, int64_t head_dim, float negative_slope,
                        float dropout_p, uint64_t seed,

@@ -176,6 +176,41 @@ def test_gat_fused_dropout_is_replayed_in_backward(oracle, cuda):
     assert abs(lhs - rhs) <= 1e-3 * (abs(lhs) + 1)
 
 
+@pytest.mark.parametrize("H,F", [(1, 16), (4, 16), (2, 40), (8, 8)])
+@pytest.mark.parametrize("thr", [16, 48, 96])
+def test_gat_hub_segments_match_cta_per_row(oracle, cuda, H, F, thr):
+    """hub rows: the segmented path (partials per segment + combine kernels) and the one-CTA-per-row path
+    are two summation orders of the same math -- forward, statistics, all three gradients, with dropout."""
+    from dgl import sparse as K
+    nn_, ne, p = 1200, 90000, 0.25
+    og, g, src, dst = graphs(oracle, nn_, nn_, ne, seed=H + F + thr, kind="powerlaw", self_loops=True)
+    rng = np.random.default_rng(thr)
+    ft = rng.standard_normal((nn_, H, F)).astype(np.float32)
+    el = rng.standard_normal((nn_, H)).astype(np.float32)
+    er = rng.standard_normal((nn_, H)).astype(np.float32)
+    gout = rng.standard_normal((nn_, H, F)).astype(np.float32)
+    res = {}
+    old_thr, old_seg = K.HUB_THRESHOLD, K.GAT_HUB_SEGMENTS
+    try:
+        K.HUB_THRESHOLD = thr
+        for seg in (True, False):
+            K.GAT_HUB_SEGMENTS = seg
+            gi = g._graph
+            rst, mx, sm, sc = K._gat_fwd(gi, t(ft), t(el), t(er), 0.2, p, 77, want_scores=True)
+            gft, gel, ger = K._gat_bwd(gi, t(ft), t(el), t(er), mx, sm, t(gout), 0.2, p, 77)
+            res[seg] = [n(x) for x in (rst, mx, sm, sc, gft, gel, ger)]
+    finally:
+        K.HUB_THRESHOLD, K.GAT_HUB_SEGMENTS = old_thr, old_seg
+    assert (og.in_degrees() > thr).sum() > 0
+    names = ("rst", "row_max", "row_sum", "scores", "grad_ft", "grad_el", "grad_er")
+    for name, a, b in zip(names, res[True], res[False]):
+        if name == "row_max":
+            assert np.array_equal(a, b)
+        else:
+            tol = 2e-5 * max(1.0, float(np.abs(b).max()))
+            assert np.abs(a - b).max() <= tol, (name, float(np.abs(a - b).max()), tol)
+
+
 def test_gat_zero_in_degree_rows(oracle, cuda):
     g = dgl.graph((torch.tensor([0, 1]), torch.tensor([2, 2])), num_nodes=4).int().to(cuda)
     ft = torch.ones((4, 2, 3), device=cuda, requires_grad=True)

@@ -67,9 +67,11 @@ REG_BUDGET = {
     "spmm_rows_kernelILi2ELi4ELi4ELi1ELi0EfEE": 80,   # copy_u_max D=602
     "spmm_rows_kernelILi4ELi1ELi2ELi0ELi3EfEE": 80,   # u_mul_e_sum with (E,1) weights, D=64
     "sddmm_dot_kernelILi2ELi4ELi5ELb0ELb0EfEE": 80,   # u_dot_v D=602
-    "gat_fwd_kernelILi4ELi1ELi1ELi4ELb0EEE": 80,      # fused GAT forward, UT = 4
-    "gat_bwd_kernelILi4ELi1ELi1ELi4ELb0ELb0EEE": 80,  # fused GAT backward (dst pass)
-    "gat_bwd_kernelILi4ELi1ELi1ELi4ELb1ELb0EEE": 80,  # fused GAT backward (src pass)
+    "gat_fwd_kernelILi4ELi1ELi1ELi4ELi0EEE": 80,      # fused GAT forward, UT = 4, ordinary rows
+    "gat_fwd_kernelILi4ELi1ELi4ELi4ELi2EEE": 80,      # ... hub-row segments, 4 heads
+    "gat_bwd_kernelILi4ELi1ELi1ELi4ELb0ELi0EEE": 80,  # fused GAT backward (dst pass)
+    "gat_bwd_kernelILi4ELi1ELi1ELi4ELb1ELi0EEE": 80,  # fused GAT backward (src pass)
+    "gat_bwd_kernelILi4ELi1ELi4ELi4ELb1ELi2EEE": 80,  # ... hub-row segments, 4 heads
 }
 
 
