@@ -658,12 +658,9 @@ static size_t gat_hub_smem(const GatParams& p, int vec, int ch, int ht) {
   return sizeof(float) * ((size_t)n_groups * ht + (size_t)kBlockThreads * ch * vec);
 }
 
-// gathers in flight per lane (U*CH): 4 by default (80-100 registers, 3 CTAs/SM measured faster than 8
-// at 2 CTAs/SM on every GAT shape but products); DGLB_GAT_UT=8 selects the heavier variant
-static int gat_ut() {
-  static int ut = [] { const char* e = getenv("DGLB_GAT_UT"); return (e && atoi(e) == 8) ? 8 : 4; }();
-  return ut;
-}
+// gathers in flight per lane (U*CH): 4 (<= 80 registers, 3 CTAs/SM).  The 8-deep variant (2 CTAs/SM) was
+// measured slower on every GAT shape once the kernels were held to 3 CTAs/SM and is no longer built.
+constexpr int kGatUT = 4;
 
 template <int VEC, int CH, int HT, int UT>
 static int launch_gat_fwd_ut(const GatParams& p, int n_hub, cudaStream_t stream) {
@@ -690,8 +687,7 @@ static int launch_gat_fwd_ut(const GatParams& p, int n_hub, cudaStream_t stream)
 
 template <int VEC, int CH, int HT>
 static int launch_gat_fwd(const GatParams& p, int n_hub, cudaStream_t stream) {
-  return gat_ut() == 4 ? launch_gat_fwd_ut<VEC, CH, HT, 4>(p, n_hub, stream)
-                       : launch_gat_fwd_ut<VEC, CH, HT, 8>(p, n_hub, stream);
+  return launch_gat_fwd_ut<VEC, CH, HT, kGatUT>(p, n_hub, stream);
 }
 
 template <int VEC, int CH, int HT, int UT>
@@ -726,8 +722,7 @@ static int launch_gat_bwd_ut(int which, const GatParams& p, int n_hub, cudaStrea
 
 template <int VEC, int CH, int HT>
 static int launch_gat_bwd(int which, const GatParams& p, int n_hub, cudaStream_t stream) {
-  return gat_ut() == 4 ? launch_gat_bwd_ut<VEC, CH, HT, 4>(which, p, n_hub, stream)
-                       : launch_gat_bwd_ut<VEC, CH, HT, 8>(which, p, n_hub, stream);
+  return launch_gat_bwd_ut<VEC, CH, HT, kGatUT>(which, p, n_hub, stream);
 }
 
 template <int VEC, int CH>
