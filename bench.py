@@ -201,10 +201,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries the JSON result line(s): keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION, printed
-        # to stdout) out of it; any more verbose setting the user chose (INFO, TRACE) is left alone
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries the JSON result line(s): send NCCL's own log (the "NCCL version ..." banner at
+        # NCCL_DEBUG >= VERSION goes to stdout by default) to stderr instead
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- workload (structure identical on every rank; rows are partitioned for N > 1)
