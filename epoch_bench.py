@@ -118,8 +118,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries the JSON result line(s): send NCCL's own log (the "NCCL version ..." banner at
-        # NCCL_DEBUG >= VERSION goes to stdout by default) to stderr instead
+        # stdout carries the JSON result line(s): send NCCL's own log (the "NCCL version ..." banner the box's
+        # NCCL_DEBUG=VERSION prints to stdout) to stderr.  NCCL honours NCCL_DEBUG_FILE only above VERSION.
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     for name in args.configs.split(","):
