@@ -56,7 +56,7 @@ def test_gathers_are_issued_as_a_batch(sass, fragment, min_run):
     assert best >= min_run, "%s: longest run of vector gathers before an FP consumer is %d (< %d)" % (fragment, best, min_run)
 
 
-# Residency guard: 256-thread CTAs need <= 80 registers per thread for 3 CTAs per SM.  Measured on the
+# Residency guard: 256-thread CTAs need <= 80 registers per thread for 3 CTAs per SM (48 for 5, 32 for 8).  Measured on the
 # products graph: copy_u_sum 2.72 ms at 70 registers vs 4.78 ms at 84; copy_u_max 4.04 ms at 98 vs 2.88 ms
 # at 80; fused GAT 1.2-1.35x from 2 -> 3 CTAs per SM (profiles/r01_notes.md sections 9-10).
 REG_BUDGET = {
@@ -72,6 +72,10 @@ REG_BUDGET = {
     "gat_bwd_kernelILi4ELi1ELi1ELi4ELb0ELi0EEE": 80,  # fused GAT backward (dst pass)
     "gat_bwd_kernelILi4ELi1ELi1ELi4ELb1ELi0EEE": 80,  # fused GAT backward (src pass)
     "gat_bwd_kernelILi4ELi1ELi4ELi4ELb1ELi2EEE": 80,  # ... hub-row segments, 4 heads
+    "edge_softmax_rows_kernelILb0ELi8ELb0EEE": 32,    # edge_softmax fwd, dst-sorted graph, R = 8: 8 CTAs/SM
+    "edge_softmax_rows_kernelILb1ELi8ELb0EEE": 32,    # ... bwd
+    "edge_softmax_rows_kernelILb0ELi16ELb0EEE": 48,   # R = 16: 5 CTAs/SM
+    "edge_softmax_rows_kernelILb1ELi16ELb0EEE": 48,
 }
 
 
