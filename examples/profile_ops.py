@@ -1,5 +1,5 @@
-"""One launch of each secondary op (for `ncu --set full -k regex:...`): copy_u_sum (the yardstick),
-copy_u_max, u_mul_e_sum with (E,1) weights, edge_softmax fwd/bwd -- on a synthetic graph of a named shape."""
+"""One launch of each secondary op (for `ncu -k regex:...`): copy_u_sum (the yardstick), copy_u_max,
+u_mul_e_sum with (E,1) weights, edge_softmax fwd/bwd, fused GAT fwd/bwd -- on a synthetic graph of a named shape."""
 import argparse
 import os
 import sys
@@ -34,6 +34,13 @@ def main():
     dgl.ops.gspmm(g, "mul", "sum", X, W)
     a = K._edge_softmax_fwd(g._graph, z)
     K._edge_softmax_bwd(g._graph, a, gr)
+    # fused GAT attention (H heads x 16), forward and both backward passes
+    H = args.heads
+    ft = torch.randn(n, H, 16, device=dev)
+    el, er = torch.randn(n, H, device=dev), torch.randn(n, H, device=dev)
+    dZ = torch.randn(n, H, 16, device=dev)
+    rst, mx, sm, _ = K._gat_fwd(g._graph, ft, el, er, 0.2, 0.0, 0)
+    K._gat_bwd(g._graph, ft, el, er, mx, sm, dZ, 0.2, 0.0, 0)
     torch.cuda.synchronize()
     print("done")
 
