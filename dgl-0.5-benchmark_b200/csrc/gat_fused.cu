@@ -598,8 +598,16 @@ __global__ void __launch_bounds__(kBlockThreads) gat_seg_feat_combine_kernel(con
   if (idx >= (int64_t)p.n_hub * p.D) return;
   const int hub = (int)(idx / p.D), k = (int)(idx - (int64_t)hub * p.D);
   const int s0 = __ldg(p.seg_ptr + hub), s1 = __ldg(p.seg_ptr + hub + 1);
-  float a = p.ws_feat[(int64_t)s0 * p.D + k];
-  for (int sg = s0 + 1; sg < s1; ++sg) a = __fadd_rn(a, p.ws_feat[(int64_t)sg * p.D + k]);
+  // a 20 000-edge row has ~160 segments: fetch 8 partials at a time (independent loads), add them in order
+  float a = 0.f;
+  for (int sg = s0; sg < s1; sg += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (sg + i < s1) ? p.ws_feat[(int64_t)(sg + i) * p.D + k] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (sg + i < s1) a = (sg + i == s0) ? v[i] : __fadd_rn(a, v[i]);
+  }
   p.out_feat[(int64_t)__ldg(p.hub_rows + hub) * p.D + k] = a;
 }
 
@@ -612,9 +620,16 @@ __global__ void __launch_bounds__(kBlockThreads) gat_seg_tot_combine_kernel(cons
   const int s0 = __ldg(p.seg_ptr + hub), s1 = __ldg(p.seg_ptr + hub + 1);
   const int64_t row = __ldg(p.hub_rows + hub);
   float t1 = 0.f, t2 = 0.f, t3 = 0.f;
-  for (int sg = s0; sg < s1; ++sg) {
-    const float* w = p.ws_tot + ((int64_t)sg * p.H + h) * 4;
-    t1 += w[0]; t2 += w[1]; t3 += w[2];
+  for (int sg = s0; sg < s1; sg += 4) {
+    float v[4][3];  // (ws_tot is only 4-byte aligned when H*F is odd: scalar loads)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float* w = p.ws_tot + ((int64_t)(sg + i) * p.H + h) * 4;
+      const bool ok = sg + i < s1;
+      v[i][0] = ok ? w[0] : 0.f; v[i][1] = ok ? w[1] : 0.f; v[i][2] = ok ? w[2] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { t1 += v[i][0]; t2 += v[i][1]; t3 += v[i][2]; }
   }
   if constexpr (!SRC_PASS) {
     p.out_pack[row * p.H + h] = make_float4(__ldg(p.er + row * p.H + h), __ldg(p.row_max + row * p.H + h),

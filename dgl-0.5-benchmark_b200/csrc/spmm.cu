@@ -336,10 +336,21 @@ __global__ void __launch_bounds__(kBlockThreads) spmm_hub_combine_kernel(const S
   float a = p.ws_val[(int64_t)s0 * p.D + kk];
   int32_t au = 0, ae = 0;
   if constexpr (RED != DGLB_REDUCE_SUM) { au = p.ws_au[(int64_t)s0 * p.D + kk]; ae = p.ws_ae[(int64_t)s0 * p.D + kk]; }
-  for (int sg = s0 + 1; sg < s1; ++sg) {
-    const int64_t o = (int64_t)sg * p.D + kk;
-    if constexpr (RED == DGLB_REDUCE_SUM) a = __fadd_rn(a, p.ws_val[o]);
-    else combine<RED>(a, au, ae, p.ws_val[o], p.ws_au[o], p.ws_ae[o]);
+  if constexpr (RED == DGLB_REDUCE_SUM) {
+    // fetch 8 partial rows at a time (independent loads), add them in segment order
+    for (int sg = s0 + 1; sg < s1; sg += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (sg + i < s1) ? p.ws_val[(int64_t)(sg + i) * p.D + kk] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (sg + i < s1) a = __fadd_rn(a, v[i]);
+    }
+  } else {
+    for (int sg = s0 + 1; sg < s1; ++sg) {
+      const int64_t o = (int64_t)sg * p.D + kk;
+      combine<RED>(a, au, ae, p.ws_val[o], p.ws_au[o], p.ws_ae[o]);
+    }
   }
   const int64_t off = row * (int64_t)p.D + kk;
   if (p.row_scale) a = __fdiv_rn(a, __ldg(p.row_scale + row));
