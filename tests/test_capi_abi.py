@@ -66,3 +66,23 @@ def test_argument_errors_are_reported_without_a_gpu(built_lib):
     assert rc == -1 and b"broadcast" in l.dglb_last_error()
     assert l.dglb_default_hub_threshold(602) == 256
     assert l.dglb_default_hub_threshold(16) == 64
+
+
+def test_host_side_helpers_of_the_hub_paths(built_lib):
+    """cut-offs and workspace sizes are pure host functions (no GPU): the values DESIGN.md / the notes quote."""
+    from dgl import _capi
+    l = _capi.lib()
+    assert [l.dglb_default_row_hub_threshold(w) for w in (16, 64, 160, 602)] == [128] * 4     # fused GAT (notes §11)
+    assert [l.dglb_default_softmax_hub_threshold(h) for h in (1, 3, 4, 8, 32, 40)] == [1024, 256, 256, 128, 64, 64]
+    # edge_softmax: (n_seg + n_hub) x heads padded to a power of two x {max|acc, sum} floats
+    assert l.dglb_edge_softmax_workspace_bytes(10, 3, 3) == (10 + 3) * 4 * 2 * 4
+    # fused GAT: per segment one partial feature row (H*F) + 4 floats per head
+    assert l.dglb_gat_hub_workspace_bytes(7, 4, 16) == 7 * (64 + 16) * 4
+    assert l.dglb_hub_workspace_bytes(5, 100, 0) == 5 * 100 * 4 and l.dglb_hub_workspace_bytes(5, 100, 1) == 5 * 100 * 12
+    # unknown gspmm flag bits are rejected (after the pointer checks, so give it non-null dummies)
+    shp = _capi.shape_arr((4,))
+    d = ctypes.c_void_p(16)
+    rc = l.dglb_gspmm_csr(4, 0, 0, 1, 1, 1, d, d, None, d, None, 1, shp, shp, d, None, None, None, 8, None, None)
+    assert rc == -1 and b"flag" in l.dglb_last_error()
+    rc = l.dglb_gspmm_csr(4, 1, 0, 1, 1, 1, d, d, None, d, None, 1, shp, shp, d, None, None, None, 1, None, None)
+    assert rc == -1 and b"accumulate" in l.dglb_last_error()
