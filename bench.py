@@ -39,9 +39,6 @@ for _p in (ROOT, PKG):
 import numpy as np  # noqa: E402
 
 N_NODES, N_EDGES = 232965, 11606919
-# dram__bytes_read.sum + dram__bytes_write.sum of the D=602 gspmm launch, from the committed
-# `ncu --set full` capture (profiles/r01_ncu_d602_final.md): 26.69 GB + 0.58 GB
-TRAFFIC_D602 = 27263905440
 WIDTHS = (64, 128, 256, 602)
 METRIC = "gspmm copy_u_sum + gsddmm u_dot_v algorithmic HBM GB/s (reddit-shaped, D=64..602)"
 
@@ -101,6 +98,23 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (gspmm copy_u_sum, D=602)
+    from the committed `ncu --set full` capture named in profiles/ncu_traffic.json.  ncu cannot run inside a
+    bench run (a number printed under a profiler is never a bench value), so this is NOT measured live: the
+    entry carries the capture it came from and the sha256 of the kernel source it was taken with; a mismatch
+    with the current source is reported as stale instead of being passed off as current."""
+    import hashlib
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None, "no committed ncu capture"
+    rec = json.load(open(path))["gspmm_copy_u_sum_d602"]
+    src = os.path.join(PKG, "csrc", "spmm.cu")
+    sha = hashlib.sha256(open(src, "rb").read()).hexdigest()[:16]
+    state = "current" if sha == rec.get("spmm_cu_sha256_16") else "stale: csrc/spmm.cu changed since the capture"
+    return int(rec["dram_bytes_per_launch"]), "%s (%s)" % (rec["from"], state)
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -116,6 +130,8 @@ def cpu_arm(steps, warmup, budget_s=20.0):
     from dgl.data import synthetic
     import ctypes
     R.build()
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    R.set_num_threads(os.cpu_count() or 1)
     cores = R.num_threads()
     src, dst = synthetic.random_edges(N_NODES, N_NODES, N_EDGES, seed=0)
     og = R.OracleGraph(src, dst, N_NODES, N_NODES)
@@ -166,6 +182,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the blocks outside the headline sweep (parity vs the full-size oracle, secondary "
+                         "kernels, epochs): quick kernel-tuning runs")
+    ap.add_argument("--no-epochs", action="store_true", help="skip the full-graph epoch block")
+    ap.add_argument("--epochs", type=int, default=9, help="epochs per config in the epoch block (first 3 are warm-up)")
     ap.add_argument("--chunks", type=int, default=2,
                     help="N>1: each operand is all-gathered in this many equal chunks and aggregated chunk by "
                          "chunk behind its gather (1 = one gather, then the exact single-kernel path)")
@@ -382,6 +403,20 @@ def main():
         cnt = torch.tensor([float(launches)], device=dev, dtype=torch.float64)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         launches = int(cnt.item())
+    # ---- blocks outside the headline sweep (every rank takes part in the epoch block's collectives)
+    peak, peak_src = measured_peak()
+    secondary = parity = epochs = None
+    if not args.no_extras:
+        import bench_extras
+        if world == 1:
+            parity = bench_extras.parity_block(src, dst, N_NODES, g, dev)
+            feats = host = host_out = None
+            torch.cuda.empty_cache()
+            secondary = bench_extras.secondary_kernels(src, dst, N_NODES, dev, peak)
+        if not args.no_epochs:
+            feats = host = host_out = g = part = None
+            torch.cuda.empty_cache()
+            epochs = bench_extras.epochs_block(rank, world, dev, epochs=max(4, args.epochs))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -390,15 +425,15 @@ def main():
     total_bytes = step_bytes(N_NODES, N_EDGES, p=1)
     value = total_bytes / (ms * 1e-3) / 1e9
     e2e_val = total_bytes / (e2e_ms * 1e-3) / 1e9
-    peak, peak_src = measured_peak()
     kb = spmm_bytes(n_dst_local, n_edges_local, 602)
+    traffic, traffic_src = ncu_traffic() if world == 1 else (None, "N>1: not captured")
     achieved = kb / (k_ms * 1e-3) / 1e9
     line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "roofline": {"bound": "hbm", "kernel": "spmm_rows_kernel<VEC=2,CH=4,copy_lhs,sum> (gspmm copy_u_sum, D=602)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_D602 if world == 1 else None, "peak_source": peak_src, "kernel_ms": k_ms,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": kb,
                          "note": ("single launch timed by its own CUDA-event pair" if world == 1 else
                                   "N>1: the event pair spans the chunk-by-chunk gather waits + aggregation of this rank's rows")},
@@ -416,6 +451,12 @@ def main():
         for v in bf16.values():
             v["frac_of_peak"] = v["algorithmic_gbs"] / peak
         line["bf16_storage"] = bf16
+    if secondary is not None:
+        line["kernels"].extend(secondary)
+    if parity is not None:
+        line["parity"] = parity
+    if epochs is not None:
+        line["epochs"] = epochs
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_arm(1, 0, budget_s=15.0)
         line["cpu_baseline"] = cb

@@ -444,12 +444,9 @@ static int launch_fast(const SpmmParams& p, int n_hub, int n_seg, cudaStream_t s
   }
   if (n_hub > 0 && n_seg > 0) {
     const size_t smem = (size_t)kBlockThreads * CH * VEC * 4 * (RED == DGLB_REDUCE_SUM ? 1 : 3);
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
+    if (smem > 48 * 1024)  // per device and cheap: set on every launch that needs it (no process-wide latch)
       DGLB_CUDA(cudaFuncSetAttribute(spmm_hub_kernel<VEC, CH, OP, RED, RMODE, T>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
     spmm_hub_kernel<VEC, CH, OP, RED, RMODE, T><<<n_seg, kBlockThreads, smem, stream>>>(p);
     DGLB_LAUNCH_CHECK("spmm_hub_kernel");
     const int64_t cblocks = ((int64_t)n_hub * p.D + kBlockThreads - 1) / kBlockThreads;

@@ -97,7 +97,16 @@ def lib():
     return _lib
 
 
+_restore_device = None  # device index to switch back to after the C-ABI call that follows an enter()
+
+
 def check(rc, what):
+    global _restore_device
+    if _restore_device is not None:
+        # enter() switched the thread's current CUDA device for an op on another GPU's tensors: switch back, so
+        # later torch allocations / current_stream() calls of a multi-GPU process stay on the caller's device
+        prev, _restore_device = _restore_device, None
+        lib().dglb_set_device(prev)
     if rc != 0:
         msg = lib().dglb_last_error().decode("utf-8", "replace")
         raise DGLError("%s failed (status %d): %s" % (what, rc, msg))
@@ -137,7 +146,14 @@ def require_cuda(*tensors):
 
 
 def enter(dev):
-    """Select the device in the library's CUDA runtime and return the current torch stream handle."""
-    idx = dev.index if dev.index is not None else torch.cuda.current_device()
-    check(lib().dglb_set_device(idx), "dglb_set_device")
+    """Make `dev` current for the C-ABI call that follows (every such call is followed by check(), which
+    restores the caller's device) and return the handle of torch's current stream on `dev`."""
+    global _restore_device
+    cur = torch.cuda.current_device()
+    idx = dev.index if dev.index is not None else cur
+    if idx != cur:
+        rc = lib().dglb_set_device(idx)
+        if rc != 0:
+            raise DGLError("dglb_set_device(%d) failed: %s" % (idx, lib().dglb_last_error().decode("utf-8", "replace")))
+        _restore_device = cur
     return torch.cuda.current_stream(idx).cuda_stream

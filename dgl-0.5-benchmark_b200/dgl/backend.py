@@ -44,6 +44,7 @@ class GSpMM(torch.autograd.Function):
         out, (argX, argY) = K._gspmm(gidx, op, reduce_op, X, Y, row_scale, zero_inf=zero_inf)
         ctx.backward_cache = gidx, op, reduce_op
         ctx.has_scale = row_scale is not None
+        ctx.zero_inf = bool(zero_inf) and reduce_op in ("max", "min")
         ctx.save_for_backward(X, Y, argX, argY, row_scale)
         return out
 
@@ -54,6 +55,13 @@ class GSpMM(torch.autograd.Function):
         dZ = dZ.contiguous()
         if row_scale is not None:  # fused mean: out = sum / deg  =>  d(sum) = dZ / deg
             dZ = (dZ / row_scale.view((-1,) + (1,) * (dZ.dim() - 1))).to(dZ.dtype)
+        if ctx.zero_inf and gidx.n_edges > 0:
+            # upstream applies where(isinf(out), 0, out) as a differentiable post-pass OUTSIDE GSpMM, which
+            # zeroes the gradient of rows without in-edges before the arg-scatter; the kernel folds that
+            # post-pass into its store (arg = 0 for such rows), so the same mask has to be applied here or
+            # node 0 / edge 0 would collect the gradient of every isolated destination row
+            empty = gidx.csc().degrees() == 0
+            dZ = dZ.masked_fill(empty.view((-1,) + (1,) * (dZ.dim() - 1)), 0)
         dX = dY = None
         if op != "copy_rhs" and ctx.needs_input_grad[3]:
             g_rev = gidx.reverse()

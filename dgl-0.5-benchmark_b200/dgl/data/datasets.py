@@ -16,7 +16,7 @@ import torch
 from . import synthetic
 
 __all__ = ["load_data", "RedditDataset", "CoraGraphDataset", "CiteseerGraphDataset", "PubmedGraphDataset",
-           "CitationGraphDataset", "SyntheticNodeDataset"]
+           "CitationGraphDataset", "SyntheticNodeDataset", "LegacyTUDataset"]
 
 
 def _scale():
@@ -26,10 +26,13 @@ def _scale():
 class SyntheticNodeDataset:
     """Node-classification dataset of a given SHAPES entry."""
 
+    synthetic = True
+
     def __init__(self, name, seed=0, degree="uniform", undirected=True, self_loop=False, as_networkx=False):
         n, e, d, c = synthetic.SHAPES[name]
         s = _scale()
         n, e = max(8, int(n * s)), max(8, int(e * s))
+        synthetic.announce_synthetic(name, "%d nodes, %d edges, %d features, %d classes, uniform random" % (n, e, d, c))
         self.name, self.num_labels, self.num_classes = name, c, c
         rng = np.random.default_rng(seed)
         if undirected:  # both directions of e/2 random undirected edges, like the citation graphs
@@ -77,6 +80,35 @@ class SyntheticNodeDataset:
 
     def __len__(self):
         return 1
+
+
+class LegacyTUDataset:
+    """dgl.data.LegacyTUDataset('ENZYMES') (main_dgl_enzymes_gcn.py:11,155): 600 small graphs of ~32.6 nodes /
+    ~62.1 undirected edges with 18 float node features and 6 classes (README.md:29); dataset[i] -> (graph, label)."""
+
+    synthetic = True
+    _SHAPES = {"ENZYMES": (600, 32.63, 18, 6)}
+
+    def __init__(self, name, **kw):
+        n, mean_nodes, feat, classes = self._SHAPES[name]
+        self.name, self._feat, self.num_labels = name, feat, classes
+        self._mean_nodes = mean_nodes
+        self._n = max(16, int(n * _scale()))
+        synthetic.announce_synthetic(name, "%d molecule-like random graphs of ~%.1f nodes, %d features, %d classes"
+                                     % (self._n, mean_nodes, feat, classes))
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        from ..heterograph import graph as make_graph
+        i = int(i)
+        # ENZYMES has ~1.9 undirected edges per node: a tree plus ~0.9 extra edges per node
+        src, dst, sizes = synthetic.molecule_like_batch(1, seed=10_000 + i, mean_nodes=self._mean_nodes, extra_edge_frac=0.9)
+        g = make_graph((torch.from_numpy(src), torch.from_numpy(dst)), num_nodes=int(sizes[0]))
+        rng = np.random.default_rng(i)
+        g.ndata["feat"] = torch.from_numpy(rng.random((int(sizes[0]), self._feat), dtype=np.float32))
+        return g, torch.tensor(int(rng.integers(0, self.num_labels)))
 
 
 def CitationGraphDataset(name, **kw):

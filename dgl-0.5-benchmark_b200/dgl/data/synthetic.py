@@ -6,7 +6,25 @@ graphs are multigraphs) and `powerlaw` (destinations drawn with Zipf-like weight
 max in-degree capped near 0.1*N, mimicking reddit's hub nodes); each in two edge orders:
 `shuffled` (the CSC edge-id permutation is non-trivial) or `dst_sorted` (identity permutation).
 """
+import sys
+
 import numpy as np
+
+_announced = set()
+
+
+def announce_synthetic(name, what):
+    """Loud one-time notice (stderr) whenever a stand-in for a real dataset NAME is instantiated: accuracy /
+    rocauc / epoch-time lines an unchanged reference script prints afterwards are for seeded random data of
+    that dataset's shape, not for the dataset.  Every stand-in object also carries `.synthetic = True`."""
+    if name in _announced:
+        return
+    _announced.add(name)
+    sys.stderr.write("[dgl-b200] WARNING: dataset '%s' is a SEEDED SYNTHETIC stand-in (%s); the real dataset is not "
+                     "available offline -- accuracies printed from it are meaningless, only shapes and timings "
+                     "carry over.\n" % (name, what))
+    sys.stderr.flush()
+
 
 # name -> (num_nodes, num_directed_edges, feature_width, num_classes)   [README.md:19-25, BASELINE.json]
 SHAPES = {

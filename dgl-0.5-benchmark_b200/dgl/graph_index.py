@@ -116,6 +116,7 @@ def build_csr(n_rows, n_cols, row, col, row_sorted=None):
                 "dglb_coo_to_csr")
     if row_sorted is None:
         flag = torch.empty(1, dtype=torch.int32, device=dev)
+        stream = _capi.enter(dev)
         _capi.check(l.dglb_is_identity_perm(nnz, _capi.ptr(data), _capi.ptr(flag), stream), "dglb_is_identity_perm")
         identity = bool(flag.item())
     else:

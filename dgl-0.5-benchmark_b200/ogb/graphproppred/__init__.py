@@ -22,12 +22,15 @@ class DglGraphPropPredDataset:
     """dataset[i] -> (graph with ndata['feat'] (n,9) / edata['feat'] (e,3) int64, label[1]);
     dataset[index_tensor] -> subset; molecule-like graphs (tree + a few ring closures)."""
 
+    synthetic = True
+
     def __init__(self, name, root="dataset", num_graphs=None):
         import os
         self.name = name
         n, self._mean_nodes, self.num_tasks = _SHAPES[name]
         scale = float(os.environ.get("DGLB200_DATA_SCALE", "1"))
         self._n = int(num_graphs or max(16, int(n * scale)))
+        synthetic.announce_synthetic(name, "%d molecule-like random graphs of ~%.1f nodes" % (self._n, self._mean_nodes))
         self.eval_metric = "rocauc" if name == "ogbg-molhiv" else "acc"
         self.num_classes = 2 if name == "ogbg-molhiv" else 37
 

@@ -7,6 +7,8 @@ from dgl.data.datasets import SyntheticNodeDataset
 class DglNodePropPredDataset:
     """dataset[0] -> (graph, labels[N,1]); .get_idx_split() -> {'train','valid','test'}; .num_classes"""
 
+    synthetic = True
+
     def __init__(self, name, root="dataset"):
         self.name = name
         key = {"ogbn-arxiv": "ogbn-arxiv", "ogbn-products": "ogbn-products", "ogbn-proteins": "ogbn-proteins"}[name]

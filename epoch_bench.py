@@ -90,6 +90,9 @@ def run_config(name, epochs, rank, world, dev, degree, unfused=False):
             for p in model.parameters():
                 dist.all_reduce(p.grad)
         opt.step()
+        if world > 1:                    # the rank's share of the global loss -> the global loss
+            loss = loss.detach().clone()
+            dist.all_reduce(loss)
         losses.append(loss.item())       # synchronises, like the OGB scripts (main_dgl_arxiv_gat.py:74)
 
     l0 = _capi.launches()

@@ -84,6 +84,9 @@ def installed():
         def mean_divisor(self):
             return self._g.in_degrees().clamp(min=1).to(torch.float32)
 
+        def degrees(self):
+            return self._g.in_degrees()
+
     GI.GraphIndex.csc = lambda self: _CscStub(self)
     try:
         yield

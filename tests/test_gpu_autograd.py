@@ -85,6 +85,35 @@ def test_gspmm_cmp_gradients(oracle, cuda, op, reduce_op):
         np.testing.assert_allclose(n(Wt.grad), W64.grad.numpy(), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("op", ["copy_lhs", "mul", "copy_rhs"])
+@pytest.mark.parametrize("reduce_op", ["max", "min"])
+def test_gspmm_cmp_gradients_with_isolated_rows(oracle, cuda, op, reduce_op):
+    """Destination rows without in-edges get out = 0 (upstream's where(isinf, 0) post-pass) and must not
+    leak their incoming gradient into node 0 / edge 0 through the arg = 0 the kernel records for them."""
+    rng = np.random.default_rng(11)
+    n_src, n_dst, n_e = 40, 60, 90               # ~22 % of the destination rows stay empty
+    src = rng.integers(0, n_src, n_e)
+    dst = rng.integers(0, n_dst, n_e)
+    dst[dst % 4 == 0] = 1                        # rows 0, 4, 8, ... are isolated for sure
+    g = dgl.create_block((torch.from_numpy(src), torch.from_numpy(dst)), n_src, n_dst).int().to("cuda")
+    assert int((g.in_degrees() == 0).sum()) >= 15
+    X = rng.standard_normal((n_src, 5)).astype(np.float32)
+    W = (rng.random((n_e, 5)) + 0.5).astype(np.float32)
+    Xt, Wt = t(X).requires_grad_(True), t(W).requires_grad_(True)
+    out = dgl.ops.gspmm(g, op, reduce_op, Xt if op != "copy_rhs" else None, Wt if op != "copy_lhs" else None)
+    gout = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+    out.backward(t(gout))
+    X64 = torch.tensor(X, dtype=torch.float64, requires_grad=True)
+    W64 = torch.tensor(W, dtype=torch.float64, requires_grad=True)
+    ref = _ref_spmm(src, dst, n_dst, op, reduce_op, X64, W64)
+    np.testing.assert_allclose(n(out), ref.detach().numpy(), rtol=1e-5, atol=1e-6)
+    ref.backward(torch.tensor(gout, dtype=torch.float64))
+    if op != "copy_rhs":
+        np.testing.assert_allclose(n(Xt.grad), X64.grad.numpy(), rtol=1e-5, atol=1e-6)
+    if op != "copy_lhs":
+        np.testing.assert_allclose(n(Wt.grad), W64.grad.numpy(), rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize("op,lt,rt,shape", [("dot", "u", "v", (64,)), ("dot", "u", "v", (4, 16)), ("add", "u", "v", (4, 1)),
                                             ("mul", "u", "v", (8,)), ("mul", "e", "v", (3,)), ("add", "e", "u", (3,)),
                                             ("sub", "u", "v", (5,)), ("div", "u", "v", (5,))])

@@ -85,3 +85,16 @@ def test_molhiv_gcn_script_runs_unchanged():
     out = _run("end_to_end/full_graph/graph_classification/main_dgl_molhiv_gcn.py",
                ["--epochs", "3", "--runs", "1", "--num_workers", "0", "--eval"], scale=0.005)
     assert "Training time/epoch" in out and "Valid:" in out, out[-2000:]
+
+
+def test_enzymes_gcn_script_runs_unchanged():
+    out = _run("end_to_end/full_graph/graph_classification/main_dgl_enzymes_gcn.py",
+               ["--epochs", "3", "--runs", "1", "--eval"], scale=0.2)
+    assert "Training time/epoch" in out and "Valid:" in out, out[-2000:]
+
+
+def test_proteins_rgcn_script_runs_unchanged():
+    # main_dgl_proteins_rgcn_for.py:46-60: update_all(u_mul_e('feat','weight'), mean) once per relation
+    out = _run("end_to_end/full_graph/node_classification/main_dgl_proteins_rgcn_for.py",
+               ["--epochs", "5", "--runs", "1", "--eval"], scale=0.0005)
+    assert "Training time/epoch" in out and "Test:" in out, out[-2000:]
