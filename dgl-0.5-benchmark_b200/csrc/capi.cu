@@ -174,7 +174,7 @@ int dglb_gspmm_csr(int op, int reduce, int dtype, int64_t n_rows, int64_t n_cols
   if (op == DGLB_OP_COPY_LHS) { for (int d = 0; d < b.ndim; ++d) { b.rhs[d] = b.lhs[d]; b.out[d] = b.lhs[d]; } b.rhs_len = b.out_len = b.lhs_len; }
   if (op == DGLB_OP_COPY_RHS) { for (int d = 0; d < b.ndim; ++d) { b.lhs[d] = b.rhs[d]; b.out[d] = b.rhs[d]; } b.lhs_len = b.out_len = b.rhs_len; }
   if (dtype == DGLB_BF16)
-    return spmm_csr_bf16(op, reduce, n_rows, indptr, indices, ufeat, b.out_len, out, row_scale, flags, hub,
+    return spmm_csr_bf16(op, reduce, n_rows, n_cols, nnz, indptr, indices, ufeat, b.out_len, out, row_scale, flags, hub,
                          static_cast<cudaStream_t>(stream));
   return spmm_csr_f32(op, reduce, n_rows, n_cols, nnz, indptr, indices, eids, static_cast<const float*>(ufeat),
                       static_cast<const float*>(efeat), b, static_cast<float*>(out), arg_u, arg_e, row_scale,
@@ -201,7 +201,6 @@ int dglb_gsddmm_csr(int op, int dtype, int lhs_target, int rhs_target, int64_t n
                     const int32_t* indptr, const int32_t* indices, const int32_t* eids, const void* lhs,
                     const void* rhs, int ndim, const int64_t* lhs_shape_host, const int64_t* rhs_shape_host,
                     void* out, const dglb_hub_t* hub, void* stream) {
-  (void)n_src;
   BcastShape b;
   int64_t rs;
   int rc = sddmm_common(op, dtype, lhs_target, rhs_target, ndim, lhs_shape_host, rhs_shape_host, lhs, rhs, out, nnz, &b, &rs);
@@ -210,7 +209,7 @@ int dglb_gsddmm_csr(int op, int dtype, int lhs_target, int rhs_target, int64_t n
   if (nnz == 0 || n_dst == 0) return DGLB_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (lhs_target == DGLB_TARGET_U && rhs_target == DGLB_TARGET_V) {
-    rc = sddmm_csr_fast_f32(op, n_dst, indptr, indices, eids, static_cast<const float*>(lhs),
+    rc = sddmm_csr_fast_f32(op, n_dst, n_src, nnz, indptr, indices, eids, static_cast<const float*>(lhs),
                             static_cast<const float*>(rhs), b, rs, static_cast<float*>(out), hub, st, dtype);
     if (rc != DGLB_E_UNSUPPORTED) return rc;
   }

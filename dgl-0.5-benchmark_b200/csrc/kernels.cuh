@@ -68,14 +68,19 @@ int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz
                  const int32_t* indices, const int32_t* eids, const float* X, const float* W,
                  const BcastShape& b, float* out, int32_t* arg_u, int32_t* arg_e, const float* row_scale,
                  int accumulate, const dglb_hub_t* hub, cudaStream_t stream);
-int spmm_csr_bf16(int op, int reduce, int64_t n_rows, const int32_t* indptr, const int32_t* indices,
-                  const void* X, int64_t D, void* out, const float* row_scale, int accumulate,
-                  const dglb_hub_t* hub, cudaStream_t stream);
+int spmm_csr_bf16(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* indptr,
+                  const int32_t* indices, const void* X, int64_t D, void* out, const float* row_scale,
+                  int accumulate, const dglb_hub_t* hub, cudaStream_t stream);
 // sddmm.cu
-int sddmm_csr_fast_f32(int op, int64_t n_dst, const int32_t* indptr, const int32_t* indices,
-                       const int32_t* eids, const float* Uf, const float* Vf, const BcastShape& b,
-                       int64_t reduce_size, float* out, const dglb_hub_t* hub, cudaStream_t stream,
-                       int dtype = DGLB_F32);
+int sddmm_csr_fast_f32(int op, int64_t n_dst, int64_t n_src, int64_t nnz, const int32_t* indptr,
+                       const int32_t* indices, const int32_t* eids, const float* Uf, const float* Vf,
+                       const BcastShape& b, int64_t reduce_size, float* out, const dglb_hub_t* hub,
+                       cudaStream_t stream, int dtype = DGLB_F32);
+// ring.cu: the non-hub rows of gspmm(copy_lhs, sum) (dot = false) or gsddmm(u_dot_v) (dot = true) through the
+// bulk-copy ring kernel; DGLB_E_UNSUPPORTED (no error set) when the shape is outside its range
+int ring_rows(bool dot, int dtype, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* indptr,
+              const int32_t* indices, const int32_t* eids, const void* X, const void* V, int64_t D, void* out,
+              const float* row_scale, int accumulate, int hub_threshold, cudaStream_t stream);
 int sddmm_generic_f32(const GenericSddmmParams& g, cudaStream_t stream);
 // edge_softmax.cu
 int edge_softmax_f32(bool bwd, int64_t n_dst, int64_t nnz, int64_t n_heads, const int32_t* indptr, const int32_t* eids,

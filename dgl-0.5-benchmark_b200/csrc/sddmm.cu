@@ -35,6 +35,7 @@ struct SddmmParams {
   int H;      // dot: number of output columns (heads)
   int seg;    // dot: lanes per head
   int hub_threshold;
+  int skip_rows;  // dot: the ordinary rows were already processed by the ring kernel (ring.cu)
 };
 
 template <int OP>
@@ -352,7 +353,7 @@ template <int VEC, int CH, int LOGG, bool SINGLE, typename T>
 static int launch_dot(const SddmmParams& p, int n_hub, cudaStream_t stream) {
   const int rows_per_block = kBlockThreads / p.G;
   const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
-  if (blocks > 0) {
+  if (blocks > 0 && !p.skip_rows) {
     sddmm_dot_kernel<VEC, CH, LOGG, SINGLE, false, T><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
     DGLB_LAUNCH_CHECK("sddmm_dot_kernel");
   }
@@ -408,9 +409,10 @@ static int dispatch_ew(const SddmmParams& p, int vec, int ch, int n_hub, cudaStr
 }
 
 // returns DGLB_E_UNSUPPORTED (without setting an error) when the vector path does not apply
-int sddmm_csr_fast_f32(int op, int64_t n_dst, const int32_t* indptr, const int32_t* indices,
-                       const int32_t* eids, const float* Uf, const float* Vf, const BcastShape& b,
-                       int64_t reduce_size, float* out, const dglb_hub_t* hub, cudaStream_t stream, int dtype) {
+int sddmm_csr_fast_f32(int op, int64_t n_dst, int64_t n_src, int64_t nnz, const int32_t* indptr,
+                       const int32_t* indices, const int32_t* eids, const float* Uf, const float* Vf,
+                       const BcastShape& b, int64_t reduce_size, float* out, const dglb_hub_t* hub,
+                       cudaStream_t stream, int dtype) {
   if (dtype == DGLB_BF16 && op != DGLB_OP_DOT) return DGLB_E_UNSUPPORTED;
   if (b.lhs_len != b.rhs_len) return DGLB_E_UNSUPPORTED;
   for (int d = 0; d < b.ndim; ++d)
@@ -427,7 +429,19 @@ int sddmm_csr_fast_f32(int op, int64_t n_dst, const int32_t* indptr, const int32
   p.seg_len = use_hub ? hub->seg_len : 0;
   p.n_rows = n_dst; p.D = (int)D;
   p.hub_threshold = use_hub ? hub->threshold : INT32_MAX;
+  p.skip_rows = 0;
   const int n_hub = use_hub ? hub->n_seg : 0;  // hub launches are sized by SEGMENTS
+  if (op == DGLB_OP_DOT && b.out_len == 1) {
+    // wide rows: whole-row bulk copies into a shared-memory ring (ring.cu); hub rows stay on the segmented path
+    const int rc = ring_rows(true, dtype, n_dst, n_src, nnz, indptr, indices, eids, Uf, Vf, D, out, nullptr, 0,
+                             p.hub_threshold, stream);
+    if (rc == DGLB_OK) {
+      if (!use_hub) return DGLB_OK;
+      p.skip_rows = 1;
+    } else if (rc != DGLB_E_UNSUPPORTED) {
+      return rc;
+    }
+  }
   int vec = dtype == DGLB_BF16 ? 8 : 4;
   if (dtype == DGLB_BF16) {
     vec = min_int(pick_vec_bf16(D, Uf), pick_vec_bf16(D, Vf));

@@ -58,6 +58,7 @@ struct SpmmParams {
   int ncols;    // D / VEC
   int G, log2G;
   int hub_threshold;
+  int skip_rows;   // the ordinary rows were already processed by the ring kernel (ring.cu): hub kernels only
   int accumulate;  // sum only: add the result to the existing contents of `out`
   int zero_inf;    // max/min only: store 0 where the result is +-inf (empty rows), as upstream's Python does
 };
@@ -438,7 +439,7 @@ template <int VEC, int CH, int OP, int RED, int RMODE, typename T = float>
 static int launch_fast(const SpmmParams& p, int n_hub, int n_seg, cudaStream_t stream) {
   const int rows_per_block = kBlockThreads / p.G;
   const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
-  if (blocks > 0) {
+  if (blocks > 0 && !p.skip_rows) {
     spmm_rows_kernel<VEC, CH, OP, RED, RMODE, T><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
     DGLB_LAUNCH_CHECK("spmm_rows_kernel");
   }
@@ -489,8 +490,6 @@ int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz
                  const int32_t* indptr, const int32_t* indices, const int32_t* eids, const float* X,
                  const float* W, const BcastShape& b, float* out, int32_t* arg_u, int32_t* arg_e,
                  const float* row_scale, int flags, const dglb_hub_t* hub, cudaStream_t stream) {
-  (void)n_cols;
-  (void)nnz;
   if (n_rows == 0 || b.out_len == 0) return DGLB_OK;
   const bool use_l = op != DGLB_OP_COPY_RHS, use_r = op != DGLB_OP_COPY_LHS;
   // ---- classify the broadcast pattern
@@ -545,6 +544,18 @@ int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz
     p.hub_threshold = use_hub ? hub->threshold : INT32_MAX;
     p.accumulate = (flags & DGLB_SPMM_ACCUMULATE) ? 1 : 0;
     p.zero_inf = (flags & DGLB_SPMM_ZERO_INF) ? 1 : 0;
+    p.skip_rows = 0;
+    if (op == DGLB_OP_COPY_LHS && reduce == DGLB_REDUCE_SUM) {
+      // wide rows: whole-row bulk copies into a shared-memory ring (ring.cu); hub rows stay on the segmented path
+      const int rc = ring_rows(false, DGLB_F32, n_rows, n_cols, nnz, indptr, indices, nullptr, X, nullptr, b.out_len,
+                               out, row_scale, p.accumulate, p.hub_threshold, stream);
+      if (rc == DGLB_OK) {
+        if (!use_hub) return DGLB_OK;
+        p.skip_rows = 1;
+      } else if (rc != DGLB_E_UNSUPPORTED) {
+        return rc;
+      }
+    }
     int vec = pick_vec(b.out_len, out);
     if (use_l) vec = and_vec(vec, pick_vec(b.out_len, X));
     if (rmode == RMODE_FULL) vec = and_vec(vec, pick_vec(b.out_len, W));
@@ -577,9 +588,9 @@ int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz
 }
 
 // bf16 storage / fp32 accumulate: copy_lhs x sum (the SAGE aggregation and the micro-benchmark op)
-int spmm_csr_bf16(int op, int reduce, int64_t n_rows, const int32_t* indptr, const int32_t* indices,
-                  const void* X, int64_t D, void* out, const float* row_scale, int accumulate,
-                  const dglb_hub_t* hub, cudaStream_t stream) {
+int spmm_csr_bf16(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* indptr,
+                  const int32_t* indices, const void* X, int64_t D, void* out, const float* row_scale,
+                  int accumulate, const dglb_hub_t* hub, cudaStream_t stream) {
   if (op != DGLB_OP_COPY_LHS || reduce != DGLB_REDUCE_SUM) {
     set_error("gspmm: bf16 storage is implemented for copy_lhs with reducer sum (mean through row_scale)");
     return DGLB_E_UNSUPPORTED;
@@ -605,6 +616,17 @@ int spmm_csr_bf16(int op, int reduce, int64_t n_rows, const int32_t* indptr, con
   }
   p.ws_au = nullptr; p.ws_ae = nullptr;
   p.hub_threshold = use_hub ? hub->threshold : INT32_MAX;
+  p.skip_rows = 0;
+  {
+    const int rc = ring_rows(false, DGLB_BF16, n_rows, n_cols, nnz, indptr, indices, nullptr, X, nullptr, D, out,
+                             row_scale, p.accumulate, p.hub_threshold, stream);
+    if (rc == DGLB_OK) {
+      if (!use_hub) return DGLB_OK;
+      p.skip_rows = 1;
+    } else if (rc != DGLB_E_UNSUPPORTED) {
+      return rc;
+    }
+  }
   const int vec = min_int(pick_vec_bf16(D, X), pick_vec_bf16(D, out));
   p.ncols = (int)(D / vec);
   p.G = group_lanes(p.ncols);

@@ -145,10 +145,12 @@ def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None, zero_inf=False):
         width = 1
         for s_ in feat_shape:
             width *= s_
-        if width >= 32 and width % 8:
+        # (wide rows on large graphs go through the bulk-copy ring kernel, which takes 4-byte-aligned rows as they are)
+        ring = width * 2 >= 1024 and width % 2 == 0 and gidx.n_edges >= (1 << 18)
+        if width >= 32 and width % 8 and not ring:
             padded = torch.nn.functional.pad(u.reshape(u.shape[0], width), (0, 8 - width % 8))
             res, _ = _gspmm(gidx, op, reduce_op, padded, None, row_scale)
-            return res[:, :width].reshape(out_shape), (None, None)
+            return res[:, :width].contiguous().reshape(out_shape), (None, None)
     arg_u = arg_e = None
     if out is not None:
         if reduce_op != "sum" or tuple(out.shape) != out_shape or not out.is_contiguous() or out.dtype != ref.dtype:
@@ -228,7 +230,8 @@ def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
         rhs = rhs.contiguous()
     feat_shape = infer_broadcast_shape(op, lhs.shape[1:] if use_lhs else (1,), rhs.shape[1:] if use_rhs else (1,))
     ref = lhs if use_lhs else rhs
-    if dtype == _capi.BF16 and lhs.dim() == 2 and lhs.shape[1] >= 32 and lhs.shape[1] % 8:
+    ring = lhs is not None and lhs.dim() == 2 and lhs.shape[1] * 2 >= 1024 and lhs.shape[1] % 2 == 0 and gidx.n_edges >= (1 << 18)
+    if dtype == _capi.BF16 and lhs.dim() == 2 and lhs.shape[1] >= 32 and lhs.shape[1] % 8 and not ring:
         pad = 8 - lhs.shape[1] % 8  # zero columns do not change the dot product; 128-bit loads instead of 32-bit
         return _gsddmm(gidx, op, torch.nn.functional.pad(lhs, (0, pad)), torch.nn.functional.pad(rhs, (0, pad)),
                        lhs_target, rhs_target)
