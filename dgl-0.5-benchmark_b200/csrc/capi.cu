@@ -111,6 +111,26 @@ int dglb_csr_find_hub_rows(int64_t n_rows, const int32_t* indptr, int32_t thresh
   return csr_find_hub_rows(n_rows, indptr, threshold, hub_rows, cap, n_hub, static_cast<cudaStream_t>(stream));
 }
 
+size_t dglb_edge_stage_plan_workspace_bytes(int64_t nnz, int log2_bucket) {
+  if (log2_bucket < 5 || log2_bucket > 24) return 0;
+  return edge_stage_plan_workspace_bytes(nnz, log2_bucket);
+}
+
+int dglb_edge_stage_plan(int64_t nnz, const int32_t* eids, int log2_bucket, int32_t* stage_pos, int32_t* slot,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  DGLB_CHECK_ARG(nnz >= 0 && log2_bucket >= 5 && log2_bucket <= 24, "edge_stage_plan: bad nnz / log2_bucket");
+  DGLB_CHECK_ARG(nnz == 0 || (eids && stage_pos && slot), "edge_stage_plan: null array");
+  return edge_stage_plan(nnz, eids, log2_bucket, stage_pos, slot, workspace, workspace_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int dglb_edge_stage(int to_staged, int64_t nnz, int64_t row_bytes, const int32_t* stage_pos, const void* src, void* dst,
+                    void* stream) {
+  DGLB_CHECK_ARG(nnz >= 0 && row_bytes >= 0 && row_bytes % 4 == 0, "edge_stage: rows must be a whole number of 4-byte words");
+  DGLB_CHECK_ARG(nnz == 0 || row_bytes == 0 || (stage_pos && src && dst && src != dst), "edge_stage: null or aliased buffers");
+  return edge_stage_move(to_staged ? 1 : 0, nnz, row_bytes / 4, stage_pos, src, dst, static_cast<cudaStream_t>(stream));
+}
+
 size_t dglb_hub_workspace_bytes(int64_t n_seg, int64_t out_len, int with_args) {
   if (n_seg <= 0 || out_len <= 0) return 0;
   return (size_t)n_seg * (size_t)out_len * 4 * (with_args ? 3 : 1);

@@ -80,8 +80,15 @@ int sddmm_csr_fast_f32(int op, int64_t n_dst, int64_t n_src, int64_t nnz, const 
 // bulk-copy ring kernel; DGLB_E_UNSUPPORTED (no error set) when the shape is outside its range
 int ring_rows(bool dot, int dtype, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* indptr,
               const int32_t* indices, const int32_t* eids, const void* X, const void* V, int64_t D, void* out,
-              const float* row_scale, int accumulate, int hub_threshold, cudaStream_t stream);
+              const float* row_scale, int accumulate, int hub_threshold, const int32_t* light_indptr,
+              cudaStream_t stream);
 int sddmm_generic_f32(const GenericSddmmParams& g, cudaStream_t stream);
+// edge_stage.cu
+size_t edge_stage_plan_workspace_bytes(int64_t nnz, int log2_bucket);
+int edge_stage_plan(int64_t nnz, const int32_t* eids, int log2_bucket, int32_t* stage_pos, int32_t* slot,
+                    void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int edge_stage_move(int to_staged, int64_t nnz, int64_t row_words, const int32_t* stage_pos, const void* src, void* dst,
+                    cudaStream_t stream);
 // edge_softmax.cu
 int edge_softmax_f32(bool bwd, int64_t n_dst, int64_t nnz, int64_t n_heads, const int32_t* indptr, const int32_t* eids,
                      const float* a, const float* b, float* out, const dglb_hub_t* hub, cudaStream_t stream);

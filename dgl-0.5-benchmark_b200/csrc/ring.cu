@@ -36,6 +36,8 @@ constexpr int kRingWarps = kRingThreads / 32;
 
 struct RingParams {
   const int32_t* __restrict__ indptr;
+  const int32_t* __restrict__ balance;  // [n_rows+1] prefix sum the warps' row ranges are cut on (indptr, or the
+                                        // prefix sum of the non-hub rows' nnz when hub rows are left to other kernels)
   const int32_t* __restrict__ indices;
   const int32_t* __restrict__ eids;     // DOT: edge id of each CSR position (null = identity)
   const unsigned char* __restrict__ X;  // gathered rows: n_cols rows of row_bytes
@@ -130,14 +132,18 @@ __device__ __forceinline__ void lds_vec(const unsigned char* src, float (&v)[VEC
   }
 }
 
-// NCH = vector columns per lane (lane l owns columns l, l+32, ...); DOT = gsddmm u_dot_v instead of gspmm sum
+// NCH = vector columns per lane (lane l owns columns l, l+32, ...); DOT = gsddmm u_dot_v instead of gspmm sum.
+// The per-edge path is kept short on purpose (ncu, first version: 200 warp instructions per edge, issue slots 54 %
+// busy at 16 resident warps, 92 registers): slot indices and phases are carried as wrapping counters instead of
+// `% S` and `/ S`, only the last vector column of a lane is range-checked, shared-memory offsets are immediates.
 template <typename T, int VEC, int NCH, bool DOT>
-__global__ void __launch_bounds__(kRingThreads, 2) ring_kernel(const RingParams p) {
+__global__ void __launch_bounds__(kRingThreads, 3) ring_kernel(const RingParams p) {
   extern __shared__ __align__(128) unsigned char ring_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.S;
-  unsigned char* slots = ring_smem + (size_t)warp * S * p.slot_bytes;
-  unsigned char* tail = ring_smem + (size_t)kRingWarps * S * p.slot_bytes;
+  const int slot_bytes = p.slot_bytes;
+  unsigned char* slots = ring_smem + (size_t)warp * S * slot_bytes;
+  unsigned char* tail = ring_smem + (size_t)kRingWarps * S * slot_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail) + warp * S;
   int* meta = reinterpret_cast<int*>(tail + (size_t)kRingWarps * S * 8) + warp * S;
   const uint32_t slots_u32 = smem_u32(slots), bars_u32 = smem_u32(bars);
@@ -148,44 +154,51 @@ __global__ void __launch_bounds__(kRingThreads, 2) ring_kernel(const RingParams 
   }
   __syncwarp();
 
-  // ---- this warp's rows: an equal share of the edges, cut at row boundaries
+  // ---- this warp's rows: an equal share of the (non-hub) edges, cut at row boundaries
   const int64_t gw = (int64_t)blockIdx.x * kRingWarps + warp, nw = (int64_t)gridDim.x * kRingWarps;
-  const int64_t r0 = gw == 0 ? 0 : row_lower_bound(p.indptr, p.n_rows, p.nnz * gw / nw);
-  const int64_t r1 = gw + 1 == nw ? p.n_rows : row_lower_bound(p.indptr, p.n_rows, p.nnz * (gw + 1) / nw);
+  const int64_t work = __ldg(p.balance + p.n_rows);
+  const int64_t r0 = gw == 0 ? 0 : row_lower_bound(p.balance, p.n_rows, work * gw / nw);
+  const int64_t r1 = gw + 1 == nw ? p.n_rows : row_lower_bound(p.balance, p.n_rows, work * (gw + 1) / nw);
   if (r0 >= r1) return;
 
   EdgeCursor pc;  // producer cursor
   pc.row = r0 - 1; pc.row_end = r1; pc.pos = pc.end = 0;
   pc.settle(p);
-  int issued = 0, consumed = 0;
-  const unsigned char* const x_last = p.X + (p.n_cols - 1) * (int64_t)p.row_bytes;
+  int in_flight = 0;            // copies requested and not yet consumed
+  int pslot = 0, cslot = 0;     // next slot to fill / to consume
+  uint32_t cphase = 0;          // parity the consumer waits for on cslot
+  const int row_bytes = p.row_bytes;
+  const int last_col = (int)p.n_cols - 1;
+  // the highest row of X: would a copy rounded up to 16 bytes read past the end of the tensor?
+  const bool last_unsafe = ((reinterpret_cast<uintptr_t>(p.X) + (uint64_t)p.n_cols * row_bytes) & 15) != 0;
+  const int lane_off = lane * VEC * (int)sizeof(T);
+  constexpr int kColStride = 32 * VEC * (int)sizeof(T);
 
   auto fill = [&]() {
-    while (pc.valid && issued - consumed < S) {
-      const int slot = issued % S;
+    while (pc.valid && in_flight < S) {
       const int c = __ldg(p.indices + pc.pos);
-      const unsigned char* g = p.X + (int64_t)c * p.row_bytes;
+      const unsigned char* g = p.X + (int64_t)c * row_bytes;
       const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15);
-      const uint32_t bytes = (shift + p.row_bytes + 15u) & ~15u;
-      if (g == x_last && bytes != shift + (uint32_t)p.row_bytes) {
-        // the highest row of X: the rounded-up copy would read past the end of the tensor -- copy it by hand
-        unsigned char* d = slots + (size_t)slot * p.slot_bytes + shift;
-        for (int i = lane * 4; i < p.row_bytes; i += 128)
+      if (c == last_col && last_unsafe) {   // copy it by hand (warp-uniform branch)
+        unsigned char* d = slots + pslot * slot_bytes + shift;
+        for (int i = lane * 4; i < row_bytes; i += 128)
           *reinterpret_cast<uint32_t*>(d + i) = __ldg(reinterpret_cast<const uint32_t*>(g + i));
         __syncwarp();
-        if (lane == 0) { meta[slot] = (int)shift; mbar_arrive(bars_u32 + 8 * slot); }
+        if (lane == 0) { meta[pslot] = (int)shift; mbar_arrive(bars_u32 + 8 * pslot); }
       } else if (lane == 0) {
-        meta[slot] = (int)shift;
-        mbar_expect_tx(bars_u32 + 8 * slot, bytes);
-        bulk_g2s(slots_u32 + slot * p.slot_bytes, g - shift, bytes, bars_u32 + 8 * slot);
+        const uint32_t bytes = (shift + row_bytes + 15u) & ~15u;
+        meta[pslot] = (int)shift;
+        mbar_expect_tx(bars_u32 + 8 * pslot, bytes);
+        bulk_g2s(slots_u32 + pslot * slot_bytes, g - shift, bytes, bars_u32 + 8 * pslot);
       }
-      ++issued;
-      ++pc.pos;
-      pc.settle(p);
+      ++in_flight;
+      if (++pslot == S) pslot = 0;
+      if (++pc.pos >= pc.end) pc.settle(p);
     }
   };
 
   const int D = p.D;
+  const int ncols = p.ncols;
   for (int64_t row = r0; row < r1; ++row) {
     const int s = __ldg(p.indptr + row), e = __ldg(p.indptr + row + 1);
     if (e - s > p.hub_threshold) continue;  // the hub kernels write this row / these edges
@@ -199,7 +212,7 @@ __global__ void __launch_bounds__(kRingThreads, 2) ring_kernel(const RingParams 
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
           const int vc = lane + 32 * c;
-          if (vc < p.ncols) {
+          if (c < NCH - 1 || vc < ncols) {
             const FVec<VEC> t = ldg_vec_t<T, VEC>(reinterpret_cast<const T*>(p.V) + row * (int64_t)D + (int64_t)vc * VEC);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acc[c][v] = t.v[v];
@@ -210,16 +223,14 @@ __global__ void __launch_bounds__(kRingThreads, 2) ring_kernel(const RingParams 
     float pending = 0.f;  // DOT: lane k holds the result of the k-th edge of the current batch of 32
     for (int j = s; j < e; ++j) {
       fill();
-      const int slot = consumed % S;
-      mbar_wait(bars_u32 + 8 * slot, (uint32_t)(consumed / S) & 1u);
-      const unsigned char* src = slots + (size_t)slot * p.slot_bytes + meta[slot];
+      mbar_wait(bars_u32 + 8 * cslot, cphase);
+      const unsigned char* src = slots + cslot * slot_bytes + meta[cslot] + lane_off;
       if constexpr (!DOT) {
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          const int vc = lane + 32 * c;
-          if (vc < p.ncols) {
+          if (c < NCH - 1 || lane + 32 * c < ncols) {
             float x[VEC];
-            lds_vec<T, VEC>(src + (size_t)vc * VEC * sizeof(T), x);
+            lds_vec<T, VEC>(src + c * kColStride, x);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acc[c][v] = __fadd_rn(acc[c][v], x[v]);
           }
@@ -228,10 +239,9 @@ __global__ void __launch_bounds__(kRingThreads, 2) ring_kernel(const RingParams 
         float part = 0.f;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
-          const int vc = lane + 32 * c;
-          if (vc < p.ncols) {
+          if (c < NCH - 1 || lane + 32 * c < ncols) {
             float x[VEC];
-            lds_vec<T, VEC>(src + (size_t)vc * VEC * sizeof(T), x);
+            lds_vec<T, VEC>(src + c * kColStride, x);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) part = fmaf(acc[c][v], x[v], part);
           }
@@ -249,14 +259,15 @@ __global__ void __launch_bounds__(kRingThreads, 2) ring_kernel(const RingParams 
         }
       }
       __syncwarp();  // every lane is done with the slot before the producer lane refills it
-      ++consumed;
+      --in_flight;
+      if (++cslot == S) { cslot = 0; cphase ^= 1u; }
     }
     if constexpr (!DOT) {
       const float scale = p.row_scale ? __ldg(p.row_scale + row) : 1.f;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const int vc = lane + 32 * c;
-        if (vc < p.ncols) {
+        if (c < NCH - 1 || vc < ncols) {
           FVec<VEC> o;
           const int64_t off = row * (int64_t)D + (int64_t)vc * VEC;
 #pragma unroll
@@ -309,7 +320,8 @@ static int dispatch_nch(const RingParams& p, size_t smem, cudaStream_t stream) {
 // case the caller runs the row-per-group kernel instead.
 int ring_rows(bool dot, int dtype, int64_t n_rows, int64_t n_cols, int64_t nnz, const int32_t* indptr,
               const int32_t* indices, const int32_t* eids, const void* X, const void* V, int64_t D, void* out,
-              const float* row_scale, int accumulate, int hub_threshold, cudaStream_t stream) {
+              const float* row_scale, int accumulate, int hub_threshold, const int32_t* light_indptr,
+              cudaStream_t stream) {
   // Where the ring pays (profiles/r02_notes.md, reddit / products shapes): the copy engine retires ~5.3 G bulk copies
   // per second chip-wide whatever their size, so a row must be >= ~2 KB for the copies not to be the bound; and rows
   // that are not 16-byte aligned (D = 602 fp32 / bf16), which the register path can only fetch with 8- or 4-byte
@@ -317,12 +329,14 @@ int ring_rows(bool dot, int dtype, int64_t n_rows, int64_t n_cols, int64_t nnz, 
   // single process can A/B them (examples/ring_tune.py, tests/test_gpu_ring.py).
   const int esz = dtype == DGLB_BF16 ? 2 : 4;
   const int64_t row_bytes = D * esz;
-  const int min_bytes = env_int("DGLB_RING_MIN_BYTES", (row_bytes % 16) ? 1024 : 2048);
+  // (bf16 u_dot_v at 1.2 KB rows is bound by the copy rate: 6.3 ms vs 4.1 ms on the padded register path)
+  const int min_bytes = env_int("DGLB_RING_MIN_BYTES", ((row_bytes % 16) && !(dot && dtype == DGLB_BF16)) ? 1024 : 2048);
   const int min_nnz = env_int("DGLB_RING_MIN_NNZ", 1 << 18);
   const int force_s = env_int("DGLB_RING_STAGES", 0);
-  // gspmm: 3 resident CTAs per SM with a 3-deep ring beat 2 CTAs with 5 slots (3.86 vs 4.15 ms at D = 602);
-  // u_dot_v (heavier consumer): the other way round (4.22 vs 4.74 ms)
-  const int smem_budget = env_int("DGLB_RING_SMEM", dot ? 100 * 1024 : 74 * 1024);
+  // Depth: throughput peaks at ~115-130 KB of rows in flight per SM and DROPS beyond it (D = 602: 3.9 ms at 48 rows in
+  // flight, 4.1 ms at 80, 5.5 ms at 72 rows over 24 warps), so the ring is 2 deep and the CTA count per SM does the rest:
+  // 3 CTAs (24 warps) for rows up to 3 KB, 2 CTAs (forced through the shared-memory request) beyond.
+  const int smem_budget = env_int("DGLB_RING_SMEM", 0);
   if (row_bytes < min_bytes || nnz < min_nnz || n_rows < 1 || n_cols < 1) return DGLB_E_UNSUPPORTED;
   if (row_bytes % 4 || (reinterpret_cast<uintptr_t>(X) & 15) || nnz >= (1LL << 31)) return DGLB_E_UNSUPPORTED;
   int vec;
@@ -335,18 +349,20 @@ int ring_rows(bool dot, int dtype, int64_t n_rows, int64_t n_cols, int64_t nnz, 
   if (ncols > 16 * 32) return DGLB_E_UNSUPPORTED;
   RingParams p;
   p.indptr = indptr; p.indices = indices; p.eids = eids;
+  p.balance = light_indptr ? light_indptr : indptr;
   p.X = static_cast<const unsigned char*>(X); p.V = static_cast<const unsigned char*>(V);
   p.out = static_cast<unsigned char*>(out); p.row_scale = row_scale;
   p.n_rows = n_rows; p.n_cols = n_cols; p.nnz = nnz;
   p.D = (int)D; p.ncols = (int)ncols; p.row_bytes = (int)row_bytes;
   p.slot_bytes = (int)((row_bytes + 15) / 16 * 16 + 16);
-  int S = force_s > 0 ? force_s : (smem_budget / kRingWarps) / (p.slot_bytes + 12);
-  if (S < 2 && force_s <= 0) S = (110 * 1024 / kRingWarps) / (p.slot_bytes + 12);   // very wide rows: 2 CTAs per SM
+  int S = force_s > 0 ? force_s : (smem_budget > 0 ? (smem_budget / kRingWarps) / (p.slot_bytes + 12) : 2);
   if (S > 16) S = 16;
   if (S < 2) return DGLB_E_UNSUPPORTED;
   p.S = S;
   p.hub_threshold = hub_threshold; p.accumulate = accumulate;
-  const size_t smem = (size_t)kRingWarps * S * (p.slot_bytes + 8 + 4);
+  size_t smem = (size_t)kRingWarps * S * (p.slot_bytes + 8 + 4);
+  if (smem > 110 * 1024) return DGLB_E_UNSUPPORTED;                       // rows beyond ~6.8 KB: register path
+  if (force_s <= 0 && smem_budget <= 0 && row_bytes > 3072 && smem < 76 * 1024) smem = 76 * 1024;   // 2 CTAs per SM
 #define DGLB_RING_VEC(TT, VV) \
   if (vec == VV) return dot ? dispatch_nch<TT, VV, true>(p, smem, stream) : dispatch_nch<TT, VV, false>(p, smem, stream);
   if (dtype == DGLB_BF16) {

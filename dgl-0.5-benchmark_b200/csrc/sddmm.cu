@@ -434,7 +434,7 @@ int sddmm_csr_fast_f32(int op, int64_t n_dst, int64_t n_src, int64_t nnz, const 
   if (op == DGLB_OP_DOT && b.out_len == 1) {
     // wide rows: whole-row bulk copies into a shared-memory ring (ring.cu); hub rows stay on the segmented path
     const int rc = ring_rows(true, dtype, n_dst, n_src, nnz, indptr, indices, eids, Uf, Vf, D, out, nullptr, 0,
-                             p.hub_threshold, stream);
+                             p.hub_threshold, use_hub ? hub->light_indptr : nullptr, stream);
     if (rc == DGLB_OK) {
       if (!use_hub) return DGLB_OK;
       p.skip_rows = 1;

@@ -548,7 +548,7 @@ int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz
     if (op == DGLB_OP_COPY_LHS && reduce == DGLB_REDUCE_SUM) {
       // wide rows: whole-row bulk copies into a shared-memory ring (ring.cu); hub rows stay on the segmented path
       const int rc = ring_rows(false, DGLB_F32, n_rows, n_cols, nnz, indptr, indices, nullptr, X, nullptr, b.out_len,
-                               out, row_scale, p.accumulate, p.hub_threshold, stream);
+                               out, row_scale, p.accumulate, p.hub_threshold, use_hub ? hub->light_indptr : nullptr, stream);
       if (rc == DGLB_OK) {
         if (!use_hub) return DGLB_OK;
         p.skip_rows = 1;
@@ -619,7 +619,7 @@ int spmm_csr_bf16(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nn
   p.skip_rows = 0;
   {
     const int rc = ring_rows(false, DGLB_BF16, n_rows, n_cols, nnz, indptr, indices, nullptr, X, nullptr, D, out,
-                             row_scale, p.accumulate, p.hub_threshold, stream);
+                             row_scale, p.accumulate, p.hub_threshold, use_hub ? hub->light_indptr : nullptr, stream);
     if (rc == DGLB_OK) {
       if (!use_hub) return DGLB_OK;
       p.skip_rows = 1;

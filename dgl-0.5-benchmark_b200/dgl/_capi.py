@@ -35,7 +35,8 @@ class HubStruct(ctypes.Structure):
     """dglb_hub_t of include/dglb200.h."""
     _fields_ = [("rows", ctypes.c_void_p), ("seg_ptr", ctypes.c_void_p), ("seg_hub", ctypes.c_void_p),
                 ("n_hub", ctypes.c_int32), ("n_seg", ctypes.c_int32), ("seg_len", ctypes.c_int32),
-                ("threshold", ctypes.c_int32), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t)]
+                ("threshold", ctypes.c_int32), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+                ("light_indptr", ctypes.c_void_p)]
 
 
 _hub_t = ctypes.POINTER(HubStruct)
@@ -50,6 +51,9 @@ _SIGNATURES = {
     "dglb_csr_degrees": (_int, [_i64, _vp, _vp, _vp]),
     "dglb_is_identity_perm": (_int, [_i64, _vp, _vp, _vp]),
     "dglb_csr_find_hub_rows": (_int, [_i64, _vp, _i32, _vp, _i64, _vp, _vp]),
+    "dglb_edge_stage_plan_workspace_bytes": (ctypes.c_size_t, [_i64, _int]),
+    "dglb_edge_stage_plan": (_int, [_i64, _vp, _int, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
+    "dglb_edge_stage": (_int, [_int, _i64, _i64, _vp, _vp, _vp, _vp]),
     "dglb_default_hub_threshold": (_i32, [_i64]),
     "dglb_default_row_hub_threshold": (_i32, [_i64]),
     "dglb_default_softmax_hub_threshold": (_i32, [_i64]),
@@ -91,7 +95,7 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.dglb_abi_version() != 1:
+        if l.dglb_abi_version() != 2:
             raise DGLError("libdglb200.so ABI version mismatch")
         _lib = l
     return _lib

@@ -19,7 +19,9 @@ class CSRView:
     """indptr / indices / eids (None == identity) over `n_rows` rows, all int32 device tensors,
     plus per-threshold hub-row lists (caller-owned metadata of the C-ABI)."""
 
-    __slots__ = ("n_rows", "n_cols", "indptr", "indices", "eids", "_hubs", "_deg", "_deg_f")
+    __slots__ = ("n_rows", "n_cols", "indptr", "indices", "eids", "_hubs", "_deg", "_deg_f", "_stage")
+
+    LOG2_STAGE_BUCKET = 15  # staged edge order: slots are shuffled inside windows of 32 K CSR positions
 
     def __init__(self, n_rows, n_cols, indptr, indices, eids):
         self.n_rows, self.n_cols = n_rows, n_cols
@@ -27,6 +29,24 @@ class CSRView:
         self._hubs = {}
         self._deg = None
         self._deg_f = None
+        self._stage = None
+
+    def stage_plan(self):
+        """(stage_pos by edge id, slot by CSR position) of the staged edge order (include/dglb200.h,
+        dglb_edge_stage_plan), or None when the edge-id permutation is the identity.  Built once, cached."""
+        if self.eids is None:
+            return None
+        if self._stage is None:
+            dev, nnz, l = self.indptr.device, self.nnz, _capi.lib()
+            stage_pos = torch.empty(nnz, dtype=torch.int32, device=dev)
+            slot = torch.empty(nnz, dtype=torch.int32, device=dev)
+            ws_bytes = l.dglb_edge_stage_plan_workspace_bytes(nnz, self.LOG2_STAGE_BUCKET)
+            ws = torch.empty(max(1, ws_bytes), dtype=torch.uint8, device=dev)
+            stream = _capi.enter(dev)
+            _capi.check(l.dglb_edge_stage_plan(nnz, _capi.ptr(self.eids), self.LOG2_STAGE_BUCKET, _capi.ptr(stage_pos),
+                                               _capi.ptr(slot), _capi.ptr(ws), ws_bytes, stream), "dglb_edge_stage_plan")
+            self._stage = (stage_pos, slot)
+        return self._stage
 
     @property
     def nnz(self):
@@ -73,7 +93,11 @@ class CSRView:
                 seg_ptr = torch.zeros(n_hub + 1, dtype=torch.int32)
                 seg_ptr[1:] = torch.from_numpy(nseg.cumsum()).to(torch.int32)
                 seg_hub = torch.repeat_interleave(torch.arange(n_hub, dtype=torch.int32), torch.from_numpy(nseg))
-                info = HubInfo(rows, seg_ptr.to(dev), seg_hub.to(dev), n_hub, int(nseg.sum()), seg_len, int(threshold))
+                # prefix sum of the non-hub rows' nnz: what the persistent ring kernels balance their warps on
+                d = self.degrees()
+                light = torch.zeros(self.n_rows + 1, dtype=torch.int32, device=dev)
+                light[1:] = torch.cumsum(torch.where(d > threshold, torch.zeros_like(d), d), 0, dtype=torch.int64).to(torch.int32)
+                info = HubInfo(rows, seg_ptr.to(dev), seg_hub.to(dev), n_hub, int(nseg.sum()), seg_len, int(threshold), light)
         self._hubs[threshold] = info
         return info
 
@@ -81,11 +105,12 @@ class CSRView:
 class HubInfo:
     """Caller-owned hub-row metadata of the C-ABI (dglb_hub_t): device arrays + counts."""
 
-    __slots__ = ("rows", "seg_ptr", "seg_hub", "n_hub", "n_seg", "seg_len", "threshold")
+    __slots__ = ("rows", "seg_ptr", "seg_hub", "n_hub", "n_seg", "seg_len", "threshold", "light_indptr")
 
-    def __init__(self, rows, seg_ptr, seg_hub, n_hub, n_seg, seg_len, threshold):
+    def __init__(self, rows, seg_ptr, seg_hub, n_hub, n_seg, seg_len, threshold, light_indptr=None):
         self.rows, self.seg_ptr, self.seg_hub = rows, seg_ptr, seg_hub
         self.n_hub, self.n_seg, self.seg_len, self.threshold = n_hub, n_seg, seg_len, threshold
+        self.light_indptr = light_indptr
 
     def struct(self, workspace=None):
         """ctypes dglb_hub_t (keep the returned object alive across the call)."""
@@ -94,6 +119,7 @@ class HubInfo:
         st.n_hub, st.n_seg, st.seg_len, st.threshold = self.n_hub, self.n_seg, self.seg_len, self.threshold
         st.workspace = workspace.data_ptr() if workspace is not None else None
         st.workspace_bytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
+        st.light_indptr = self.light_indptr.data_ptr() if self.light_indptr is not None else None
         return st
 
 

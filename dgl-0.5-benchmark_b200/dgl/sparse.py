@@ -42,6 +42,30 @@ def _hub_arg(info, dev=None, out_len=0, with_args=False):
     return ctypes.byref(st), (st, ws), (2 if out_len else 1)
 
 
+# Staged edge order (include/dglb200.h, dglb_edge_stage_plan): on graphs whose CSC / CSR carries a non-trivial edge-id
+# permutation, narrow per-edge tensors are moved into "staged" order by one cheap pass and the kernels address them
+# through the plan's `slot` array, so a 4..64-byte per-edge access no longer costs a 128-byte DRAM line.
+# It pays once the per-edge tensor no longer fits the 126 MB L2 (reddit shape, E = 11.6 M: (E,1) weights = 46 MB are
+# L2-resident and the extra pass costs more than it saves; (E,4) scores = 186 MB and everything on the products
+# shape win 1.3-1.6x -- profiles/r02_notes.md).  Tests lower the cut-off.
+STAGE_MIN_BYTES = 96 << 20
+# Per-edge rows wider than this are addressed directly: measured on the products shape (profiles/r02_notes.md), (E,1)
+# operands / results gain 1.3-2.5x, (E,4) ones lose 5-8 % in gspmm / gsddmm (a 16-byte access already uses half a
+# sector pair) but still gain 1.2x in edge_softmax.  A second pass that brings the tensor all the way into CSR-position
+# order (so the kernels run with eids = NULL) was measured too and loses to the single staging pass everywhere.
+STAGE_MAX_ROW_FLOATS = 2
+STAGE_MAX_ROW_FLOATS_SOFTMAX = 8
+
+
+def _stage_plan(view, row_floats, max_floats=None):
+    if max_floats is None:
+        max_floats = STAGE_MAX_ROW_FLOATS
+    if (view.eids is None or row_floats < 1 or row_floats > max_floats
+            or view.nnz * row_floats * 4 < STAGE_MIN_BYTES):
+        return None
+    return view.stage_plan()
+
+
 def infer_broadcast_shape(op, shp1, shp2):
     """Feature shape of op(lhs, rhs) under numpy-style broadcasting of the per-node / per-edge
     feature shapes (leading node/edge dim excluded).  `dot` reduces the last dim to 1."""
@@ -173,10 +197,15 @@ def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None, zero_inf=False):
         thr = _hub_threshold(out_len)
         hub, _keep, hub_launches = _hub_arg(csc.hubs(thr), dev, out_len, use_cmp)
         ndim, ls, rs = _shapes_for_abi(op, u, e)
+        eids = csc.eids
+        if use_e and not use_cmp and dtype == _capi.F32:   # max / min record eids as arg_e: they need the real ids
+            plan = _stage_plan(csc, e.numel() // max(e.shape[0], 1))
+            if plan is not None:
+                e, eids = _stage_move(plan, e, True), plan[1]
         stream = _capi.enter(dev)
         rc = l.dglb_gspmm_csr(_capi.OPS[op], _capi.REDUCERS[reduce_op], dtype,
                               csc.n_rows, csc.n_cols, csc.nnz,
-                              _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(csc.eids),
+                              _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(eids),
                               _capi.ptr(u), _capi.ptr(e), ndim, ls, rs,
                               _capi.ptr(v), _capi.ptr(arg_u), _capi.ptr(arg_e), _capi.ptr(row_scale),
                               (1 if out is not None else 0) | (2 if (zero_inf and use_cmp) else 0), hub, stream)
@@ -230,7 +259,7 @@ def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
         rhs = rhs.contiguous()
     feat_shape = infer_broadcast_shape(op, lhs.shape[1:] if use_lhs else (1,), rhs.shape[1:] if use_rhs else (1,))
     ref = lhs if use_lhs else rhs
-    ring = lhs is not None and lhs.dim() == 2 and lhs.shape[1] * 2 >= 1024 and lhs.shape[1] % 2 == 0 and gidx.n_edges >= (1 << 18)
+    ring = lhs is not None and lhs.dim() == 2 and lhs.shape[1] * 2 >= 2048 and lhs.shape[1] % 2 == 0 and gidx.n_edges >= (1 << 18)
     if dtype == _capi.BF16 and lhs.dim() == 2 and lhs.shape[1] >= 32 and lhs.shape[1] % 8 and not ring:
         pad = 8 - lhs.shape[1] % 8  # zero columns do not change the dot product; 128-bit loads instead of 32-bit
         return _gsddmm(gidx, op, torch.nn.functional.pad(lhs, (0, pad)), torch.nn.functional.pad(rhs, (0, pad)),
@@ -239,7 +268,6 @@ def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
     if gidx.n_edges > 0 and out.numel() > 0:
         l = _capi.lib()
         ndim, ls, rs = _shapes_for_abi(op, lhs, rhs)
-        stream = _capi.enter(dev)
         lt, rt = _TARGET[lhs_target], _TARGET[rhs_target]
         fmts = gidx.formats()
         use_csr = ("csc" in fmts) and ((lhs_target == "u" and rhs_target == "v") or "coo" not in fmts)
@@ -250,14 +278,25 @@ def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
                 width *= s
             thr = _hub_threshold(width)
             hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
+            # narrow results (u_dot_v, u_add_v on (N,H,1) scores) on a shuffled graph: the kernel writes them in
+            # staged order (stores stay inside a 32 K-slot window), one pass then puts them in edge-id order
+            plan = None
+            if lhs_target == "u" and rhs_target == "v" and dtype == _capi.F32:
+                plan = _stage_plan(csc, out.numel() // gidx.n_edges)
+            dest = torch.empty_like(out) if plan is not None else out
+            stream = _capi.enter(dev)
             rc = l.dglb_gsddmm_csr(_capi.OPS[op], dtype, lt, rt, csc.n_rows, csc.n_cols, csc.nnz,
-                                   _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(csc.eids),
-                                   _capi.ptr(lhs), _capi.ptr(rhs), ndim, ls, rs, _capi.ptr(out),
+                                   _capi.ptr(csc.indptr), _capi.ptr(csc.indices),
+                                   _capi.ptr(plan[1] if plan is not None else csc.eids),
+                                   _capi.ptr(lhs), _capi.ptr(rhs), ndim, ls, rs, _capi.ptr(dest),
                                    hub, stream)
             _capi.check(rc, "dglb_gsddmm_csr")
             _capi.count_launch(1 + hub_launches)
+            if plan is not None:
+                out = _stage_move(plan, dest, False)
         else:
             s32, d32 = gidx.coo32()
+            stream = _capi.enter(dev)
             rc = l.dglb_gsddmm_coo(_capi.OPS[op], _capi.F32, lt, rt, gidx.n_src, gidx.n_dst, gidx.n_edges,
                                    _capi.ptr(s32), _capi.ptr(d32), _capi.ptr(lhs), _capi.ptr(rhs), ndim, ls, rs,
                                    _capi.ptr(out), stream)
@@ -287,18 +326,24 @@ def _edge_softmax_fwd(gidx, logits):
     if logits.shape[0] != gidx.n_edges:
         raise DGLError("edge_softmax: expect %d edge rows, got %d" % (gidx.n_edges, logits.shape[0]))
     logits = logits.contiguous()
-    out = torch.empty_like(logits)
     if gidx.n_edges == 0:
-        return out
+        return torch.empty_like(logits)
     heads = logits.numel() // gidx.n_edges
     csc = gidx.csc()
     l = _capi.lib()
     hub, _keep, hub_launches = _softmax_hub_arg(csc, heads, dev)
+    plan = _stage_plan(csc, heads, STAGE_MAX_ROW_FLOATS_SOFTMAX)
+    eids = csc.eids
+    if plan is not None:
+        logits, eids = _stage_move(plan, logits, True), plan[1]
+    out = torch.empty_like(logits)
     stream = _capi.enter(dev)
-    rc = l.dglb_edge_softmax_fwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(csc.eids),
+    rc = l.dglb_edge_softmax_fwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(eids),
                                  _capi.ptr(logits), _capi.ptr(out), hub, stream)
     _capi.check(rc, "dglb_edge_softmax_fwd")
     _capi.count_launch(1 + hub_launches)
+    if plan is not None:
+        out = _stage_move(plan, out, False)
     return out
 
 
@@ -314,11 +359,17 @@ def _edge_softmax_bwd(gidx, out, grad_out):
     csc = gidx.csc()
     l = _capi.lib()
     hub, _keep, hub_launches = _softmax_hub_arg(csc, heads, dev)
+    plan = _stage_plan(csc, heads, STAGE_MAX_ROW_FLOATS_SOFTMAX)
+    eids = csc.eids
+    if plan is not None:
+        out, grad_out, eids = _stage_move(plan, out, True), _stage_move(plan, grad_out, True), plan[1]
     stream = _capi.enter(dev)
-    rc = l.dglb_edge_softmax_bwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(csc.eids),
+    rc = l.dglb_edge_softmax_bwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(eids),
                                  _capi.ptr(out), _capi.ptr(grad_out), _capi.ptr(grad), hub, stream)
     _capi.check(rc, "dglb_edge_softmax_bwd")
     _capi.count_launch(1 + hub_launches)
+    if plan is not None:
+        grad = _stage_move(plan, grad, False)
     return grad
 
 

@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--order", default="shuffled")
     ap.add_argument("--softmax-heads", default="", help="comma list: also time edge_softmax fwd/bwd with H heads")
     ap.add_argument("--hub-bytes", type=int, default=0, help="override: hub threshold = hub_bytes / (4*D)")
+    ap.add_argument("--stage-min-mb", type=int, default=-1, help="override dgl.sparse.STAGE_MIN_BYTES (MB); huge = staging off")
+    ap.add_argument("--heads", default="", help="comma list H: also time u_add_v (N,H,1), u_mul_e (N,H,16)x(E,H,1), u_dot_v (N,H,16)")
     ap.add_argument("--softmax-hub", default="", help="comma list of edge_softmax hub cut-offs (edges) to sweep; 0 = default")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -47,7 +49,22 @@ def main():
     peak, _ = measured_peak()
     p = 0 if args.order == "dst_sorted" else 1
     from dgl import sparse as K
-    for D in [int(x) for x in args.widths.split(",")]:
+    if args.stage_min_mb >= 0:
+        K.STAGE_MIN_BYTES = args.stage_min_mb << 20
+    for H in [int(x) for x in args.heads.split(",") if x]:
+        F = 16
+        el, er = torch.randn(n, H, 1, device=dev), torch.randn(n, H, 1, device=dev)
+        ft, a = torch.randn(n, H, F, device=dev), torch.rand(e, H, 1, device=dev)
+        res = {"shape": args.shape, "edges": e, "H": H, "F": F, "order": args.order, "stage_min_mb": args.stage_min_mb}
+        for name, fn, B in (
+                ("u_add_v(N,H,1)", lambda: dgl.ops.gsddmm(g, "add", el, er), 4 * (n + 1) + 4 * e + 4 * p * e + 8 * H * e + 4 * H * n),
+                ("u_mul_e_sum(N,H,F)x(E,H,1)", lambda: dgl.ops.gspmm(g, "mul", "sum", ft, a), spmm_bytes(n, e, H * F) + 4 * H * e + 4 * p * e),
+                ("u_dot_v(N,H,F)", lambda: dgl.ops.gsddmm(g, "dot", ft, ft), 4 * (n + 1) + 8 * e * p + 4 * e + 4 * H * F * (e + n) + 4 * H * e)):
+            ms = timeit(fn, reps=5)
+            res[name] = {"ms": round(ms, 4), "gbs": round(B / ms / 1e6), "frac": round(B / ms / 1e6 / peak, 3)}
+        print(json.dumps(res), flush=True)
+        del el, er, ft, a
+    for D in [int(x) for x in args.widths.split(",") if x]:
         K.HUB_THRESHOLD = max(32, args.hub_bytes // (4 * D)) if args.hub_bytes else None
         X, V = torch.rand(n, D, device=dev), torch.rand(n, D, device=dev)
         W = torch.rand(e, 1, device=dev)

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DGLB_ABI_VERSION 1
+#define DGLB_ABI_VERSION 2
 
 /* status codes */
 #define DGLB_OK 0
@@ -130,6 +130,10 @@ int32_t dglb_default_softmax_hub_threshold(int64_t n_heads);
  *   seg_ptr  [n_hub+1]  first segment of each hub row (prefix sum of ceil(nnz/seg_len))
  *   seg_hub  [n_seg]    index into rows[] of the hub row a segment belongs to
  *   workspace           device scratch of >= dglb_hub_workspace_bytes(n_seg, out_len, with_args)
+ *   light_indptr [n_rows+1]  (optional, may be NULL) prefix sum of the nnz of the NON-hub rows (hub rows count 0): the
+ *                       persistent ring kernels (wide-row gspmm copy_lhs/sum, gsddmm u_dot_v) cut the rows into equal
+ *                       shares of THEIR work with it; without it they balance on indptr, which on a hub-heavy graph
+ *                       leaves the warps whose range is mostly hub edges idle (2x on a power-law reddit shape)
  * All arrays are device pointers owned by the caller. */
 typedef struct dglb_hub_t {
   const int32_t* rows;
@@ -138,8 +142,31 @@ typedef struct dglb_hub_t {
   int32_t n_hub, n_seg, seg_len, threshold;
   void* workspace;
   size_t workspace_bytes;
+  const int32_t* light_indptr;
 } dglb_hub_t;
 size_t dglb_hub_workspace_bytes(int64_t n_seg, int64_t out_len, int with_args);
+
+/* ---------------------------------------------------------------- staged edge order
+ * (new; upstream addresses per-edge operands as efeat[data[j]] / out[data[j]] directly: cuda/spmm.cuh, sddmm.cuh.)
+ * When the edges of a graph were not created in CSC (CSR) order, `eids` is a random permutation and every narrow
+ * per-edge access W[eids[j]] costs a 128-byte DRAM line.  dglb_edge_stage_plan derives from `eids` (the `data` array
+ * of dglb_coo_to_csr) a second permutation that is the identity up to a shuffle INSIDE buckets of 2^log2_bucket
+ * consecutive CSR positions:
+ *   stage_pos[e]  staged slot of edge id e            (bucket of slot == bucket of the edge's CSR position)
+ *   slot[j]       staged slot of CSR position j       (= stage_pos[eids[j]]; inside a bucket, slots are in edge-id order)
+ * dglb_edge_stage moves a per-edge tensor of `row_bytes`-byte rows between edge-id order and staged order in one pass
+ * (to_staged = 1: dst[stage_pos[e]] = src[e]; 0: dst[e] = src[stage_pos[e]]) at ~3 x row_bytes of DRAM traffic per edge.
+ * The compute entry points are then called with `slot` as their `eids` argument and the staged tensor as the per-edge
+ * operand / output: inside a kernel every per-edge access stays within a 2^log2_bucket-slot window of its CSR position.
+ * Entry points that also use `eids` as a NAME (arg_e of max/min, the dropout counter of the fused GAT kernels) must be
+ * given the real edge ids.  Recommended log2_bucket: 15.
+ */
+size_t dglb_edge_stage_plan_workspace_bytes(int64_t nnz, int log2_bucket);
+int dglb_edge_stage_plan(int64_t nnz, const int32_t* eids, int log2_bucket,
+                         int32_t* stage_pos /* nnz, by edge id */, int32_t* slot /* nnz, by CSR position */,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int dglb_edge_stage(int to_staged, int64_t nnz, int64_t row_bytes, const int32_t* stage_pos,
+                    const void* src, void* dst, void* stream);
 
 /* ---------------------------------------------------------------- generalized SpMM
  * replaces upstream FFI `_CAPI_DGLKernelSpMM` (src/array/kernel.cc::SpMM ->

@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     lib = ctypes.CDLL(built_lib)
     for name in _header_functions():
         assert hasattr(lib, name), "libdglb200.so does not export %s" % name
-    assert lib.dglb_abi_version() == 1
+    assert lib.dglb_abi_version() == 2
 
 
 def test_ctypes_signatures_match_header_arity(built_lib):
