@@ -187,8 +187,13 @@ def main():
                          "kernels, epochs): quick kernel-tuning runs")
     ap.add_argument("--no-epochs", action="store_true", help="skip the full-graph epoch block")
     ap.add_argument("--epochs", type=int, default=9, help="epochs per config in the epoch block (first 3 are warm-up)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: p2p = ring-ordered peer pulls through symmetric memory (copy engines over NVLink), "
+                         "aggregated one peer-group block at a time; nccl = chunked all_gather_into_tensor")
+    ap.add_argument("--peer-groups", default="", help="p2p: comma list of block sizes by ring distance (sums to N); "
+                                                      "default RowPartition.default_peer_groups(N)")
     ap.add_argument("--chunks", type=int, default=2,
-                    help="N>1: each operand is all-gathered in this many equal chunks and aggregated chunk by "
+                    help="nccl exchange: each operand is all-gathered in this many equal chunks and aggregated chunk by "
                          "chunk behind its gather (1 = one gather, then the exact single-kernel path)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -197,7 +202,9 @@ def main():
     config = {"workload": "reddit-shaped uniform random multigraph N=232965 E=11606919 (shuffled edge order), "
                           "gspmm copy_u_sum + gsddmm u_dot_v, D in {64,128,256,602}, fp32/int32",
               "partition": ("none" if world == 1 else
-                            "1-D rows over %d ranks, operands all-gathered in %d chunks" % (world, args.chunks)),
+                            ("1-D rows over %d ranks, %s" % (world, "operands pulled peer-to-peer in ring order "
+                             "(symmetric memory, copy engines), aggregated per peer-group block" if args.exchange == "p2p"
+                             else "operands all-gathered over NCCL in %d chunks" % args.chunks))),
               "l2": "no explicit flush: the sweep touches 2.0 GB of features per step, >> 126 MB L2, between reuses"}
 
     if args.impl == "reference":
@@ -233,7 +240,13 @@ def main():
     src, dst = synthetic.random_edges(N_NODES, N_NODES, N_EDGES, seed=0)
     if world > 1:
         from dgl.distributed_rows import RowPartition
-        part = RowPartition.build(src, dst, N_NODES, world, rank, dev, chunks=max(1, args.chunks))
+        if args.exchange == "p2p":
+            groups = ([int(x) for x in args.peer_groups.split(",")] if args.peer_groups
+                      else RowPartition.default_peer_groups(world))
+            part = RowPartition.build(src, dst, N_NODES, world, rank, dev, chunks=1, peer_groups=groups).enable_p2p()
+            config["peer_groups"] = groups
+        else:
+            part = RowPartition.build(src, dst, N_NODES, world, rank, dev, chunks=max(1, args.chunks))
         g = part.local_graph
         n_dst_local, n_edges_local = part.n_local_rows, part.n_local_edges
     else:
@@ -266,7 +279,17 @@ def main():
                 out = timed(("gspmm_copy_u_sum", D), record, lambda: dgl.ops.gspmm(g, "copy_lhs", "sum", X, None))
                 sc = timed(("gsddmm_u_dot_v", D), record, lambda: dgl.ops.gsddmm(g, "dot", X, V))
             return out, sc
-        # N > 1: widest operand first; the gathers of operand i+1 are queued on the NCCL stream before
+        if part.p2p:
+            # all four exchanges are queued on the copy stream up front, narrowest operand first, so the first block
+            # can be aggregated after a few microseconds and the wide operands travel behind the narrow ones' compute
+            order = sorted(WIDTHS)
+            gath = part.p2p_gather([feats[D][0] for D in order])
+            for D, (buf, evs) in zip(order, gath):
+                V = feats[D][1]
+                out = timed(("gspmm_copy_u_sum", D), record, lambda: part.blocked_copy_u_sum(buf, evs))
+                sc = timed(("gsddmm_u_dot_v", D), record, lambda: part.blocked_u_dot_v(buf, evs, V))
+            return out, sc
+        # nccl: widest operand first; the gathers of operand i+1 are queued on the NCCL stream before
         # operand i is aggregated, and each operand is aggregated chunk by chunk behind its own gather
         order = sorted(WIDTHS, reverse=True)
         pending = part.all_gather_rows(feats[order[0]][0], async_op=True)
@@ -341,6 +364,16 @@ def main():
                         host_out[D][0].copy_(out, non_blocking=True)
                     s_main.wait_event(ev_)
                     sc = dgl.ops.gsddmm(g, "dot", X, V)
+                elif part.p2p:
+                    (buf, evs), = part.p2p_gather([X])
+                    out = part.blocked_copy_u_sum(buf, evs)
+                    c1 = torch.cuda.Event()
+                    c1.record(s_main)
+                    s_out.wait_event(c1)
+                    with torch.cuda.stream(s_out):
+                        host_out[D][0].copy_(out, non_blocking=True)
+                    s_main.wait_event(ev_)
+                    sc = torch.cat(part.blocked_u_dot_v(buf, evs, V), 0)
                 else:
                     out, buf = part.pipelined_copy_u_sum(X)
                     c1 = torch.cuda.Event()

@@ -30,6 +30,19 @@ queued on the communication stream up front; the compute stream aggregates block
 k has landed, accumulating into the output (`dglb_gspmm_csr(..., accumulate=1)`), so gather k+1
 travels while block k is aggregated.  The block order changes the summation order: this path
 matches the exact path to tolerance, not bit for bit.
+
+Peer-to-peer exchange (enable_p2p; the path bench.py and the epoch models use on NVLink boxes).  NCCL's all-gather is
+a kernel that occupies SMs and delivers every shard at the same time, so nothing can be aggregated until the whole
+collective has landed (8 GPUs, D = 602: 0.93 ms exposed in front of a 0.68 ms kernel).  Here every rank publishes its
+rows in a symmetric-memory buffer (torch.distributed._symmetric_memory: the peers' buffers are mapped into this
+process over NVLink) and PULLS the other shards with plain device-to-device copies on a side stream -- copy engines,
+no SMs -- in ring order: step k fetches the shard of rank (r + k) mod P, so in every step each GPU serves exactly one
+reader at full link rate and shard k lands after k/(P-1) of the exchange.  The rank's CSC slice is pre-split by the
+ring distance of the source's owner into a few column blocks (`peer_groups`, e.g. [1, 3, 4]: local rows | the next
+three peers | the last four); block g is aggregated as soon as its last shard has landed (CUDA events, no spinning
+kernels), accumulating into the output, while the later shards are still in flight.  The local block needs no
+communication at all.  Block order changes the summation order (tolerance, not bit-identity); exact=True waits for
+every shard and runs the single-kernel path instead.
 """
 import numpy as np
 import torch
@@ -72,6 +85,12 @@ class RowPartition:
         self.n_local_edges = 0
         self._fwd_geid = self._bwd_geid = None   # global edge ids of the two blocks, in block order
         self._geid_cache = {}
+        self.peer_blocks = None      # [(block graph, last ring step it needs)] forward blocks by owner ring distance
+        self.peer_blocks_bwd = None  # the same split of the backward block
+        self._p2p = None             # (trailing shape, dtype) -> (symmetric tensor, handle, [peer views], gather buffer)
+        self._p2p_group = None
+        self._copy_stream = None
+        self.exact = True            # peer-to-peer autograd path: single-kernel (bit-identical) or blocked aggregation
 
     # ------------------------------------------------------------------ construction
     def pad_ids(self, ids):
@@ -84,7 +103,38 @@ class RowPartition:
         return (k * self.world + own) * self.chunk_rows + (local - k * self.chunk_rows), k
 
     @staticmethod
-    def build(src, dst, n_nodes, world, rank, device, chunks=1, group=None):
+    def default_peer_groups(world):
+        """Column blocks by ring distance of the source's owner: the local rows, then a few groups of peers --
+        enough blocks to start early, few enough that re-reading the partial output stays cheap."""
+        if world <= 1:
+            return [1]
+        if world == 2:
+            return [1, 1]
+        if world <= 4:
+            return [1, 1, world - 2]
+        rest = world - 1
+        a = rest // 3
+        return [1, a, a, rest - 2 * a]
+
+    def ring_step_of(self, ids):
+        """ring distance (owner - rank) mod P of the owner of each global node id"""
+        his = np.array([r[1] for r in self.ranges])
+        own = np.searchsorted(his, ids, side="right")
+        return (own - self.rank) % self.world
+
+    def _split_by_ring_step(self, cols_global, s_pad, d_loc, device, groups):
+        step = self.ring_step_of(cols_global)
+        blocks, lo = [], 0
+        for gsz in groups:
+            m = (step >= lo) & (step < lo + gsz)
+            blocks.append((create_block((torch.from_numpy(s_pad[m]), torch.from_numpy(d_loc[m])), self.n_pad,
+                                        self.n_local_rows).int().to(device), lo + gsz - 1))
+            lo += gsz
+        assert lo == self.world, "peer_groups must sum to the world size"
+        return blocks
+
+    @staticmethod
+    def build(src, dst, n_nodes, world, rank, device, chunks=1, group=None, peer_groups=None):
         src = np.asarray(src, dtype=np.int64)
         dst = np.asarray(dst, dtype=np.int64)
         indeg = np.bincount(dst, minlength=n_nodes)
@@ -102,6 +152,11 @@ class RowPartition:
         # destination nodes (whose dZ rows are gathered) and the "destinations" the local source nodes
         part.bwd_graph = create_block((torch.from_numpy(part.pad_ids(dst[selb])[0]), torch.from_numpy(src[selb] - lo)),
                                       part.n_pad, hi - lo).int().to(device)
+        if peer_groups is not None:
+            assert chunks == 1, "peer blocks use the one-slot-per-rank gather layout"
+            part.peer_blocks = part._split_by_ring_step(src[sel], s_pad, d_loc, device, peer_groups)
+            part.peer_blocks_bwd = part._split_by_ring_step(dst[selb], part.pad_ids(dst[selb])[0], src[selb] - lo, device,
+                                                            peer_groups)
         if chunks > 1:
             part.chunk_blocks = []
             for k in range(chunks):
@@ -130,6 +185,110 @@ class RowPartition:
             else:
                 works.append(None)
         return (out, works) if async_op else out
+
+    # ------------------------------------------------------------------ peer-to-peer exchange (symmetric memory)
+    def enable_p2p(self, group=None):
+        """Switch the exchange to ring-ordered peer pulls through symmetric memory (CUDA + NCCL process group)."""
+        assert self.chunks == 1, "the peer-to-peer exchange uses the one-slot-per-rank gather layout"
+        self._p2p, self._p2p_group = {}, (group if group is not None else dist.group.WORLD)
+        self._copy_stream = torch.cuda.Stream()
+        return self
+
+    @property
+    def p2p(self):
+        return self._p2p is not None
+
+    def _p2p_slot(self, x, nth=0):
+        """Symmetric buffer, handle and peer views for row tensors shaped like x (nth: n-th operand of that shape in
+        one exchange).  The first call per key is a collective (rendezvous): every rank must make it in the same order."""
+        key = (tuple(x.shape[1:]), x.dtype, nth)
+        if key not in self._p2p:
+            import torch.distributed._symmetric_memory as symm_mem
+            shape = (self.chunk_rows,) + key[0]
+            t = symm_mem.empty(shape, dtype=key[1], device=x.device)
+            hdl = symm_mem.rendezvous(t, self._p2p_group)
+            views = [hdl.get_buffer(r, shape, key[1]) if r != self.rank else t for r in range(self.world)]
+            self._p2p[key] = (t, hdl, views)
+        return self._p2p[key]
+
+    def p2p_gather(self, xs):
+        """Start the exchange of a list of local row tensors.  Returns [(buffer, events)] per operand: the padded
+        gather buffer (the local shard is in place in stream order) and events[k], k = 1..P-1, which fire once the
+        shard of rank (rank + k) mod P has landed.  Two device-side barriers per call (not per operand): peers have
+        finished reading what the symmetric buffers held before / every rank has published its new rows."""
+        P, cr, main = self.world, self.chunk_rows, torch.cuda.current_stream()
+        seen, slots, gbufs = {}, [], []
+        for x in xs:
+            k = (tuple(x.shape[1:]), x.dtype)
+            slots.append(self._p2p_slot(x, seen.get(k, 0)))
+            seen[k] = seen.get(k, 0) + 1
+            # fresh gather buffer (caching allocator): callers may keep it for their backward pass
+            gbufs.append(torch.empty((self.n_pad,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device))
+        hdl0 = slots[0][1]
+        hdl0.barrier(channel=0)
+        for x, (t, _, _), gbuf in zip(xs, slots, gbufs):
+            x = x.contiguous()
+            t[: x.shape[0]].copy_(x)
+            gbuf[self.rank * cr: self.rank * cr + x.shape[0]].copy_(x)
+        hdl0.barrier(channel=1)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        out = []
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            for x, (t, _, views), gbuf in zip(xs, slots, gbufs):
+                gbuf.record_stream(self._copy_stream)
+                events = [None] * P
+                for k in range(1, P):
+                    peer = (self.rank + k) % P
+                    n_peer = self.sizes[peer]
+                    if n_peer:
+                        gbuf[peer * cr: peer * cr + n_peer].copy_(views[peer][:n_peer], non_blocking=True)
+                    events[k] = torch.cuda.Event()
+                    events[k].record(self._copy_stream)
+                out.append((gbuf, events))
+        return out
+
+    @staticmethod
+    def _wait(events, upto):
+        pending = [events[k] for k in range(1, upto + 1) if events[k] is not None]
+        if pending:
+            cur = torch.cuda.current_stream()
+            for ev in pending:
+                cur.wait_event(ev)
+
+    def blocked_copy_u_sum(self, buf, events, exact=False, bwd=False):
+        """gspmm(copy_lhs, sum) of the rank's rows from a gather in flight: one column block per peer group, each as
+        soon as its shards have landed (exact=True: wait for everything, single kernel, bit-identical)."""
+        g_all = self.bwd_graph if bwd else self.local_graph
+        blocks = self.peer_blocks_bwd if bwd else self.peer_blocks
+        small = buf.numel() * buf.element_size() // max(self.world, 1) < self.MIN_PIPELINE_CHUNK_BYTES
+        if exact or blocks is None or small:
+            self._wait(events, self.world - 1)
+            return K_._gspmm(g_all._graph, "copy_lhs", "sum", buf, None)[0]
+        out = None
+        for blk, last in blocks:
+            self._wait(events, last)
+            if blk.number_of_edges() == 0 and out is not None:
+                continue
+            if out is None:
+                out = K_._gspmm(blk._graph, "copy_lhs", "sum", buf, None)[0]
+            else:
+                K_._gspmm(blk._graph, "copy_lhs", "sum", buf, None, out=out)
+        return out
+
+    def blocked_u_dot_v(self, buf, events, v_local):
+        """gsddmm(dot) for the rank's edges, one peer-group block at a time; returns the per-block (E_g, 1) results
+        (block g holds the edges whose source is owned by a rank of group g, in global edge order)."""
+        small = buf.numel() * buf.element_size() // max(self.world, 1) < self.MIN_PIPELINE_CHUNK_BYTES
+        if self.peer_blocks is None or small:
+            self._wait(events, self.world - 1)
+            return [K_._gsddmm(self.local_graph._graph, "dot", buf, v_local)]
+        outs = []
+        for blk, last in self.peer_blocks:
+            self._wait(events, last)
+            outs.append(K_._gsddmm(blk._graph, "dot", buf, v_local))
+        return outs
 
     def unpad(self, gathered):
         """(N, ...) tensor in global node order from a padded gather buffer (tests / debugging)."""
@@ -223,6 +382,12 @@ class _PartitionedCopyUSum(torch.autograd.Function):
     def forward(ctx, part, x_local, reduce_op):
         ctx.part, ctx.reduce_op = part, reduce_op
         with torch.no_grad():
+            if part.p2p:
+                (buf, ev), = part.p2p_gather([x_local])
+                out = part.blocked_copy_u_sum(buf, ev, exact=part.exact)
+                if reduce_op == "mean":
+                    out = out / part.local_graph._graph.csc().mean_divisor().view(-1, 1)
+                return out
             x_full = part.all_gather_rows(x_local)
             out = ops.gspmm(part.local_graph, "copy_lhs", reduce_op, x_full, None)
         return out
@@ -235,6 +400,9 @@ class _PartitionedCopyUSum(torch.autograd.Function):
             if ctx.reduce_op == "mean":
                 deg = part.local_graph.in_degrees().clamp(min=1).to(dz_local.dtype)
                 dz_local = dz_local / deg.view(-1, 1)
+            if part.p2p:
+                (buf, ev), = part.p2p_gather([dz_local])
+                return None, part.blocked_copy_u_sum(buf, ev, exact=part.exact, bwd=True), None
             dz_full = part.all_gather_rows(dz_local)
             dx = ops.gspmm(part.bwd_graph, "copy_lhs", "sum", dz_full, None)
         return None, dx, None
@@ -244,8 +412,12 @@ class _PartitionedGAT(torch.autograd.Function):
     @staticmethod
     def forward(ctx, part, ft, el, er, slope, dropout_p, seed):
         with torch.no_grad():
-            ft_full = part.all_gather_rows(ft)
-            el_full = part.all_gather_rows(el)
+            if part.p2p:
+                (ft_full, _), (el_full, ev) = part.p2p_gather([ft, el])
+                part._wait(ev, part.world - 1)       # the copy stream is in order: el's last shard is the last of both
+            else:
+                ft_full = part.all_gather_rows(ft)
+                el_full = part.all_gather_rows(el)
             rst, row_max, row_sum, _ = K_._gat_fwd(part.local_graph._graph, ft_full, el_full, er.contiguous(), slope,
                                                    dropout_p, seed, eids=part.global_eids("fwd"))
         ctx.part, ctx.args = part, (slope, dropout_p, seed)
@@ -259,10 +431,17 @@ class _PartitionedGAT(torch.autograd.Function):
         ft, el, er, ft_full, el_full, row_max, row_sum = ctx.saved_tensors
         with torch.no_grad():
             grad_rst = grad_rst.contiguous()
+            if part.p2p:   # grad_rst is known now: it travels while the destination pass runs
+                (grad_full, ev_g), = part.p2p_gather([grad_rst])
             row_pack, grad_er = K_._gat_bwd_dst(part.local_graph._graph, ft_full, el_full, er.contiguous(), row_max,
                                                 row_sum, grad_rst, slope, dropout_p, seed, eids=part.global_eids("fwd"))
-            pack_full = part.all_gather_rows(row_pack)
-            grad_full = part.all_gather_rows(grad_rst)
+            if part.p2p:
+                (pack_full, ev_p), = part.p2p_gather([row_pack])
+                part._wait(ev_g, part.world - 1)
+                part._wait(ev_p, part.world - 1)
+            else:
+                pack_full = part.all_gather_rows(row_pack)
+                grad_full = part.all_gather_rows(grad_rst)
             # the backward block's CSC has the LOCAL SOURCE nodes as rows and padded destination ids as columns
             grad_ft, grad_el = K_._gat_bwd_src(part.bwd_graph._graph.csc(), ft.contiguous(), el.contiguous(), pack_full,
                                                grad_full, slope, dropout_p, seed, eids=part.global_eids("bwd"))

@@ -52,7 +52,13 @@ def run_config(name, epochs, rank, world, dev, degree, unfused=False):
     n_edges = len(src)
     if world > 1:
         from dgl.distributed_rows import RowPartition
-        part = RowPartition.build(src, dst, n, world, rank, dev)
+        if os.environ.get("DGLB_EXCHANGE", "p2p") == "p2p":
+            # ring-ordered peer pulls through symmetric memory, aggregation per peer-group block behind the copies
+            part = RowPartition.build(src, dst, n, world, rank, dev, peer_groups=RowPartition.default_peer_groups(world))
+            part.enable_p2p()
+            part.exact = False
+        else:
+            part = RowPartition.build(src, dst, n, world, rank, dev)
         graph = part
         lo, hi = part.lo, part.hi
         feats, labels = feats[lo:hi].to(dev), labels[lo:hi].to(dev)

@@ -138,6 +138,80 @@ def test_chunk_pipelined_path_matches_single_process(oracle, world):
         np.testing.assert_allclose(got_dots, np.sort(want_dot[sel].ravel()), rtol=1e-6)
 
 
+def _peer_worker(rank, world, port, q):
+    import sys
+    for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_backend
+    from dgl.distributed_rows import RowPartition
+    n, e, D = 331, 6000, 8
+    src, dst = make_edges(n, n, e, seed=7, kind="powerlaw")
+    X = np.random.default_rng(2).random((n, D), dtype=np.float32)
+    with oracle_backend.installed():
+        groups = RowPartition.default_peer_groups(world)
+        part = RowPartition.build(src, dst, n, world, rank, torch.device("cpu"), peer_groups=groups)
+        part.MIN_PIPELINE_CHUNK_BYTES = 0
+        xl = torch.from_numpy(X[part.lo:part.hi])
+        buf = part.all_gather_rows(xl)              # same one-slot-per-rank layout the peer pulls fill on NVLink
+        ev = [None] * world
+        out = part.blocked_copy_u_sum(buf, ev)
+        exact = part.blocked_copy_u_sum(buf, ev, exact=True)
+        dx = part.blocked_copy_u_sum(buf, ev, bwd=True)
+        dots = part.blocked_u_dot_v(buf, ev, xl)
+        steps = [(b.number_of_edges(), last) for b, last in part.peer_blocks]
+        # ring distance of every block's sources
+        ok = True
+        lo_step = 0
+        cr = part.chunk_rows
+        for (b, last), gsz in zip(part.peer_blocks, groups):
+            s_pad = b.edges()[0].numpy()
+            owner = s_pad // cr
+            st = (owner - rank) % world
+            ok = ok and bool(((st >= lo_step) & (st <= last)).all())
+            lo_step += gsz
+    q.put((rank, part.lo, part.hi, out.numpy(), exact.numpy(), dx.numpy(), [d.numpy() for d in dots], steps, ok,
+           int(part.n_local_edges)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_group_blocks_match_single_process(oracle, world):
+    """The column blocks of the peer-to-peer exchange (by ring distance of the source's owner) partition the rank's
+    edges, only hold sources of their own peer group, and their accumulated aggregation equals the single-process
+    result (tolerance: block order is not edge order); exact=True is bit-identical.  The transport here is gloo's
+    all-gather into the same padded layout the NVLink peer pulls fill."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n, e, D = 331, 6000, 8
+    src, dst = make_edges(n, n, e, seed=7, kind="powerlaw")
+    X = np.random.default_rng(2).random((n, D), dtype=np.float32)
+    og = oracle.OracleGraph(src, dst, n, n)
+    want = oracle.gspmm(og, "copy_lhs", "sum", X, None)
+    want_dx = oracle.gspmm(og.reverse(), "copy_lhs", "sum", X, None)
+    want_dot = oracle.gsddmm(og, "dot", X, X)
+    np.testing.assert_allclose(np.concatenate([r[3] for r in res]), want, rtol=1e-5, atol=1e-6)
+    assert np.array_equal(np.concatenate([r[4] for r in res]), want)
+    np.testing.assert_allclose(np.concatenate([r[5] for r in res]), want_dx, rtol=1e-5, atol=1e-6)
+    for r in res:
+        assert r[8]                                                   # every block only reads its own peer group
+        assert sum(k for k, _ in r[7]) == r[9]                        # blocks partition the rank's edges
+        assert [last for _, last in r[7]][-1] == world - 1
+        sel = (dst >= r[1]) & (dst < r[2])
+        np.testing.assert_allclose(np.sort(np.concatenate(r[6]).ravel()), np.sort(want_dot[sel].ravel()), rtol=1e-6)
+
+
 def test_balanced_row_ranges():
     from dgl.distributed_rows import balanced_row_ranges
     deg = np.array([10, 0, 0, 10, 1, 1, 1, 1, 6, 10])
