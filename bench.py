@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: p2p = ring-ordered peer pulls through symmetric memory (copy engines over NVLink), "
                          "aggregated one peer-group block at a time; nccl = chunked all_gather_into_tensor")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="N>1, p2p: launch every step eagerly instead of replaying one captured CUDA graph of the step")
     ap.add_argument("--peer-groups", default="", help="p2p: comma list of block sizes by ring distance (sums to N); "
                                                       "default RowPartition.default_peer_groups(N)")
     ap.add_argument("--chunks", type=int, default=2,
@@ -282,13 +284,18 @@ def main():
         if part.p2p:
             # all four exchanges are queued on the copy stream up front, narrowest operand first, so the first block
             # can be aggregated after a few microseconds and the wide operands travel behind the narrow ones' compute
+            # The blocks are aggregated peer group by peer group across the four operands (the local blocks of all of
+            # them need no communication and run while the first shards travel), in the order the pulls are queued.
             order = sorted(WIDTHS)
             gath = part.p2p_gather([feats[D][0] for D in order])
-            for D, (buf, evs) in zip(order, gath):
-                V = feats[D][1]
-                out = timed(("gspmm_copy_u_sum", D), record, lambda: part.blocked_copy_u_sum(buf, evs))
-                sc = timed(("gsddmm_u_dot_v", D), record, lambda: part.blocked_u_dot_v(buf, evs, V))
-            return out, sc
+            outs, dots = [None] * len(order), [[] for _ in order]
+            for gi in range(part.n_blocks()):
+                for oi, D in enumerate(order):
+                    buf, evs = gath[oi]
+                    V = feats[D][1]
+                    outs[oi] = timed(("gspmm_copy_u_sum", D), record, lambda: part.block_copy_u_sum(buf, evs, gi, outs[oi]))
+                    dots[oi].append(timed(("gsddmm_u_dot_v", D), record, lambda: part.block_u_dot_v(buf, evs, gi, V)))
+            return outs, dots
         # nccl: widest operand first; the gathers of operand i+1 are queued on the NCCL stream before
         # operand i is aggregated, and each operand is aggregated chunk by chunk behind its own gather
         order = sorted(WIDTHS, reverse=True)
@@ -313,17 +320,45 @@ def main():
         for _ in range(args.warmup):
             one_step()
         barrier()
+        # N > 1, p2p: a step is ~90 copy / event / kernel launches for ~2 ms of device work, i.e. launch-bound from
+        # Python: capture ONE step (barriers, publishes, peer pulls on the copy stream, block kernels) in a CUDA
+        # graph and replay it K times.  Same work, same data movement, one launch per step.
+        step_graph = None
+        if part is not None and part.p2p and not args.no_graph:
+            try:
+                step_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(step_graph):
+                    graph_out = one_step()
+                step_graph.replay()
+                barrier()
+            except Exception as ex:  # noqa: BLE001
+                sys.stderr.write("[bench] CUDA-graph capture of the step failed (%s); launching eagerly\n" % (ex,))
+                step_graph = None
+                torch.cuda.synchronize()
+        config["step_launch"] = "cuda-graph replay" if step_graph is not None else "eager"
         l0 = _capi.launches()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local_rank) as clocks:
             start.record()
             for _ in range(args.steps):
-                one_step(record=True)
+                if step_graph is not None:
+                    step_graph.replay()
+                else:
+                    one_step(record=True)
             end.record()
             barrier()
         ms = start.elapsed_time(end) / args.steps
         launches = _capi.launches() - l0
-        per_kernel = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in ev.items()}
+        if step_graph is not None:
+            # per-launch breakdown: the same steps launched eagerly with an event pair around every op (the graph
+            # replays above cannot carry timing events); these figures include Python launch gaps
+            l1 = _capi.launches()
+            for _ in range(args.steps):
+                one_step(record=True)
+            barrier()
+            launches = _capi.launches() - l1
+        # (N > 1, p2p: an op is several block launches per step -- sum them per step)
+        per_kernel = {k: float(np.sum([a.elapsed_time(b) for a, b in v]) / args.steps) for k, v in ev.items()}
         k_ms = per_kernel[("gspmm_copy_u_sum", 602)]
 
         # ---- e2e: host inputs, H2D + compute + D2H inside the timed region (public API)

@@ -89,7 +89,8 @@ class RowPartition:
         self.peer_blocks_bwd = None  # the same split of the backward block
         self._p2p = None             # (trailing shape, dtype) -> (symmetric tensor, handle, [peer views], gather buffer)
         self._p2p_group = None
-        self._copy_stream = None
+        self._copy_streams = None
+        self.peer_group_sizes = None
         self.exact = True            # peer-to-peer autograd path: single-kernel (bit-identical) or blocked aggregation
 
     # ------------------------------------------------------------------ construction
@@ -154,6 +155,7 @@ class RowPartition:
                                       part.n_pad, hi - lo).int().to(device)
         if peer_groups is not None:
             assert chunks == 1, "peer blocks use the one-slot-per-rank gather layout"
+            part.peer_group_sizes = list(peer_groups)
             part.peer_blocks = part._split_by_ring_step(src[sel], s_pad, d_loc, device, peer_groups)
             part.peer_blocks_bwd = part._split_by_ring_step(dst[selb], part.pad_ids(dst[selb])[0], src[selb] - lo, device,
                                                             peer_groups)
@@ -191,7 +193,9 @@ class RowPartition:
         """Switch the exchange to ring-ordered peer pulls through symmetric memory (CUDA + NCCL process group)."""
         assert self.chunks == 1, "the peer-to-peer exchange uses the one-slot-per-rank gather layout"
         self._p2p, self._p2p_group = {}, (group if group is not None else dist.group.WORLD)
-        self._copy_stream = torch.cuda.Stream()
+        # two copy streams: consecutive pulls alternate between them so one copy's start-up latency hides behind
+        # the other's transfer (28 pulls of 7-70 MB per step at 8 GPUs)
+        self._copy_streams = [torch.cuda.Stream(), torch.cuda.Stream()]
         return self
 
     @property
@@ -233,21 +237,33 @@ class RowPartition:
         hdl0.barrier(channel=1)
         ready = torch.cuda.Event()
         ready.record(main)
-        out = []
-        with torch.cuda.stream(self._copy_stream):
-            self._copy_stream.wait_event(ready)
-            for x, (t, _, views), gbuf in zip(xs, slots, gbufs):
-                gbuf.record_stream(self._copy_stream)
-                events = [None] * P
-                for k in range(1, P):
+        # pull order: peer group by peer group (the order the blocks are aggregated in), inside a group operand by
+        # operand; without peer groups operand by operand
+        groups, lo = [], 0
+        for gsz in (self.peer_group_sizes or [P]):
+            groups.append([k for k in range(lo, min(lo + gsz, P)) if k > 0])   # ring step 0 is the local shard
+            lo += gsz
+        all_events = [[None] * P for _ in xs]
+        for st in self._copy_streams:
+            st.wait_event(ready)
+        i = 0
+        for steps in groups:
+            for oi, (x, (t, _, views), gbuf) in enumerate(zip(xs, slots, gbufs)):
+                for k in steps:
                     peer = (self.rank + k) % P
                     n_peer = self.sizes[peer]
-                    if n_peer:
-                        gbuf[peer * cr: peer * cr + n_peer].copy_(views[peer][:n_peer], non_blocking=True)
-                    events[k] = torch.cuda.Event()
-                    events[k].record(self._copy_stream)
-                out.append((gbuf, events))
-        return out
+                    st = self._copy_streams[i % len(self._copy_streams)]
+                    i += 1
+                    with torch.cuda.stream(st):
+                        if n_peer:
+                            gbuf[peer * cr: peer * cr + n_peer].copy_(views[peer][:n_peer], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(st)
+                    all_events[oi][k] = ev
+        for gbuf in gbufs:
+            for st in self._copy_streams:
+                gbuf.record_stream(st)
+        return [(gbuf, ev) for gbuf, ev in zip(gbufs, all_events)]
 
     @staticmethod
     def _wait(events, upto):
@@ -276,6 +292,40 @@ class RowPartition:
             else:
                 K_._gspmm(blk._graph, "copy_lhs", "sum", buf, None, out=out)
         return out
+
+    def n_blocks(self):
+        return len(self.peer_blocks) if self.peer_blocks is not None else 1
+
+    def _is_small(self, buf):
+        return (self.peer_blocks is None
+                or buf.numel() * buf.element_size() // max(self.world, 1) < self.MIN_PIPELINE_CHUNK_BYTES)
+
+    def block_copy_u_sum(self, buf, events, gi, out):
+        """Block gi of blocked_copy_u_sum (for callers that interleave the blocks of several operands): returns the
+        running output.  Small operands are aggregated in one piece at the last block index."""
+        if self._is_small(buf):
+            if gi != self.n_blocks() - 1:
+                return out
+            self._wait(events, self.world - 1)
+            return K_._gspmm(self.local_graph._graph, "copy_lhs", "sum", buf, None)[0]
+        blk, last = self.peer_blocks[gi]
+        self._wait(events, last)
+        if out is None:
+            return K_._gspmm(blk._graph, "copy_lhs", "sum", buf, None)[0]
+        if blk.number_of_edges():
+            K_._gspmm(blk._graph, "copy_lhs", "sum", buf, None, out=out)
+        return out
+
+    def block_u_dot_v(self, buf, events, gi, v_local):
+        """Block gi of blocked_u_dot_v; None when the block is folded into the last one (small operands)."""
+        if self._is_small(buf):
+            if gi != self.n_blocks() - 1:
+                return None
+            self._wait(events, self.world - 1)
+            return K_._gsddmm(self.local_graph._graph, "dot", buf, v_local)
+        blk, last = self.peer_blocks[gi]
+        self._wait(events, last)
+        return K_._gsddmm(blk._graph, "dot", buf, v_local)
 
     def blocked_u_dot_v(self, buf, events, v_local):
         """gsddmm(dot) for the rank's edges, one peer-group block at a time; returns the per-block (E_g, 1) results
