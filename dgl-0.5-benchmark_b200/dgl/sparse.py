@@ -66,6 +66,18 @@ def _stage_plan(view, row_floats, max_floats=None):
     return view.stage_plan()
 
 
+def _stage_move(plan, t, to_staged):
+    """Edge-id order -> staged order (to_staged) or back, for a contiguous float32 per-edge tensor (E, ...)."""
+    out = torch.empty_like(t)
+    n = t.shape[0]
+    row_bytes = (t.numel() // n) * t.element_size()
+    stream = _capi.enter(t.device)
+    _capi.check(_capi.lib().dglb_edge_stage(1 if to_staged else 0, n, row_bytes, _capi.ptr(plan[0]), _capi.ptr(t),
+                                            _capi.ptr(out), stream), "dglb_edge_stage")
+    _capi.count_launch(1)
+    return out
+
+
 def infer_broadcast_shape(op, shp1, shp2):
     """Feature shape of op(lhs, rhs) under numpy-style broadcasting of the per-node / per-edge
     feature shapes (leading node/edge dim excluded).  `dot` reduces the last dim to 1."""
