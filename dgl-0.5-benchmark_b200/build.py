@@ -51,8 +51,39 @@ def build(force=False, verbose_ptxas=False):
     if force or jobs or _newer(LIB, objs):
         # extern "C" entry points are exported explicitly (visibility=hidden elsewhere)
         subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    build_torch_extension(force=force or bool(jobs))
     return LIB
+
+
+TORCH_LIB = os.path.join(HERE, "lib", "libdglb200_torch.so")
+
+
+def build_torch_extension(force=False):
+    """g++ -> lib/libdglb200_torch.so: the TORCH_LIBRARY("dglb200") ops of csrc_torch/ops.cpp, linked against
+    lib/libdglb200.so (rpath $ORIGIN) and torch's own libraries.  No CUDA code is compiled here: the extension
+    only needs torch's stream / allocator / device-guard headers."""
+    import torch
+    from torch.utils import cpp_extension as ce
+    src = os.path.join(HERE, "csrc_torch", "ops.cpp")
+    deps = [src, os.path.join(HERE, "..", "include", "dglb200.h"), LIB]
+    if not (force or _newer(TORCH_LIB, deps)):
+        return TORCH_LIB
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", src, "-o", TORCH_LIB,
+           "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI), "-DUSE_CUDA",
+           "-I" + os.path.join(cuda_home, "include")]
+    cmd += ["-isystem" + p for p in ce.include_paths()]
+    for lp in ce.library_paths():
+        cmd += ["-L" + lp, "-Wl,-rpath," + lp]
+    cmd += ["-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch",
+            "-L" + os.path.dirname(LIB), "-ldglb200", "-Wl,-rpath,$ORIGIN", "-Wl,--no-as-needed"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("building the torch extension failed")
+    return TORCH_LIB
 
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose_ptxas="--verbose-ptxas" in sys.argv))
+    print(TORCH_LIB)

@@ -1,8 +1,13 @@
-"""ctypes binding of the C-ABI in include/dglb200.h (lib/libdglb200.so).
+"""The door from Python into the sm_100a kernels.
 
-This is the only door from Python into the sm_100a kernels.  There is NO CPU or PyTorch
-fallback behind it: if the shared library is missing, or an op is asked to run on tensors that
-are not on a CUDA device, the call raises.  torch is used for device memory and streams only.
+Product path: `ops()` loads lib/libdglb200_torch.so -- the PyTorch C++ extension (TORCH_LIBRARY "dglb200",
+csrc_torch/ops.cpp) that allocates outputs, takes torch's current stream under a device guard and calls the C-ABI of
+include/dglb200.h in lib/libdglb200.so -- and `call()` runs one of its ops, turning the extension's RuntimeError into
+DGLError.  There is NO CPU or PyTorch fallback behind it: if a library is missing, or an op is asked to run on
+tensors that are not on a CUDA device, the call raises.
+
+`lib()` is a plain ctypes binding of the same C-ABI; the product does not use it any more -- it is what
+tests/test_capi_abi.py checks the header, the exports and the argument validation through.
 """
 import ctypes
 import os
@@ -18,7 +23,10 @@ TARGETS = {"u": 0, "e": 1, "v": 2}
 F32 = 0
 BF16 = 1
 
+TORCH_LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libdglb200_torch.so")
+
 _lib = None
+_ops = None
 _launches = 0  # number of C-ABI compute calls issued (bench.py reports kernel launches from this)
 
 
@@ -102,6 +110,34 @@ def lib():
 
 
 _restore_device = None  # device index to switch back to after the C-ABI call that follows an enter()
+
+
+def ops():
+    """torch.ops.dglb200 (loads lib/libdglb200_torch.so, which pulls in lib/libdglb200.so).  Fails loudly if absent."""
+    global _ops
+    if _ops is None:
+        for path in (LIB_PATH, TORCH_LIB_PATH):
+            if not os.path.exists(path):
+                raise DGLError(
+                    "native library %s not found: build it with `python dgl-0.5-benchmark_b200/build.py` "
+                    "(there is no CPU / PyTorch fallback for the sparse kernels)" % path)
+        torch.ops.load_library(TORCH_LIB_PATH)
+        o = torch.ops.dglb200
+        if o.abi_version() != 2:
+            raise DGLError("libdglb200.so ABI version mismatch")
+        _ops = o
+    return _ops
+
+
+def call(fn, *args):
+    """Run an op of the extension; its RuntimeError (bad argument, CUDA error, non-CUDA tensor) becomes DGLError."""
+    try:
+        return fn(*args)
+    except RuntimeError as ex:
+        raise DGLError(str(ex).split("\n")[0]) from None
+
+
+NO_HUB = (None, None, None, None, [])
 
 
 def check(rc, what):

@@ -37,15 +37,7 @@ class CSRView:
         if self.eids is None:
             return None
         if self._stage is None:
-            dev, nnz, l = self.indptr.device, self.nnz, _capi.lib()
-            stage_pos = torch.empty(nnz, dtype=torch.int32, device=dev)
-            slot = torch.empty(nnz, dtype=torch.int32, device=dev)
-            ws_bytes = l.dglb_edge_stage_plan_workspace_bytes(nnz, self.LOG2_STAGE_BUCKET)
-            ws = torch.empty(max(1, ws_bytes), dtype=torch.uint8, device=dev)
-            stream = _capi.enter(dev)
-            _capi.check(l.dglb_edge_stage_plan(nnz, _capi.ptr(self.eids), self.LOG2_STAGE_BUCKET, _capi.ptr(stage_pos),
-                                               _capi.ptr(slot), _capi.ptr(ws), ws_bytes, stream), "dglb_edge_stage_plan")
-            self._stage = (stage_pos, slot)
+            self._stage = tuple(_capi.call(_capi.ops().edge_stage_plan, self.eids, self.LOG2_STAGE_BUCKET))
         return self._stage
 
     @property
@@ -54,12 +46,7 @@ class CSRView:
 
     def degrees(self):
         if self._deg is None:
-            deg = torch.empty(self.n_rows, dtype=torch.int32, device=self.indptr.device)
-            if self.n_rows:
-                stream = _capi.enter(self.indptr.device)
-                _capi.check(_capi.lib().dglb_csr_degrees(self.n_rows, _capi.ptr(self.indptr), _capi.ptr(deg), stream),
-                            "dglb_csr_degrees")
-            self._deg = deg
+            self._deg = _capi.call(_capi.ops().csr_degrees, self.indptr)
         return self._deg
 
     def mean_divisor(self):
@@ -76,13 +63,8 @@ class CSRView:
         info = None
         if self.nnz > threshold:  # otherwise no row can exceed it: no kernel, no sync (small batched graphs)
             dev = self.indptr.device
-            n_hub_t = torch.zeros(1, dtype=torch.int32, device=dev)
             cap = max(1, min(self.n_rows, self.nnz // max(threshold, 1) + 1))
-            rows = torch.empty(cap, dtype=torch.int32, device=dev)
-            stream = _capi.enter(dev)
-            _capi.check(_capi.lib().dglb_csr_find_hub_rows(self.n_rows, _capi.ptr(self.indptr), int(threshold),
-                                                           _capi.ptr(rows), cap, _capi.ptr(n_hub_t), stream),
-                        "dglb_csr_find_hub_rows")
+            rows, n_hub_t = _capi.call(_capi.ops().find_hub_rows, self.indptr, int(threshold), cap)
             n_hub = int(n_hub_t.item())  # one-off sync per (graph, threshold)
             assert n_hub <= cap
             if n_hub:
@@ -112,6 +94,12 @@ class HubInfo:
         self.n_hub, self.n_seg, self.seg_len, self.threshold = n_hub, n_seg, seg_len, threshold
         self.light_indptr = light_indptr
 
+    def pack(self):
+        """The hub arguments of the extension's ops: (rows, seg_ptr, seg_hub, light_indptr, [n_hub, n_seg, seg_len,
+        threshold]); workspaces are allocated by the op."""
+        return (self.rows, self.seg_ptr, self.seg_hub, self.light_indptr,
+                [self.n_hub, self.n_seg, self.seg_len, self.threshold])
+
     def struct(self, workspace=None):
         """ctypes dglb_hub_t (keep the returned object alive across the call)."""
         st = _capi.HubStruct()
@@ -127,24 +115,11 @@ def build_csr(n_rows, n_cols, row, col, row_sorted=None):
     """Stable sort of (row, col) by row on the device -> CSRView.  `row_sorted` (True/False/None):
     whether `row` is already non-decreasing, i.e. the edge-id permutation is the identity; when it is
     known from the host side (graphs created from CPU tensors) the device check and its sync are skipped."""
-    dev = row.device
     _capi.require_cuda(row, col)
-    nnz = row.shape[0]
-    indptr = torch.empty(n_rows + 1, dtype=torch.int32, device=dev)
-    indices = torch.empty(nnz, dtype=torch.int32, device=dev)
-    data = torch.empty(nnz, dtype=torch.int32, device=dev)
-    l = _capi.lib()
-    ws_bytes = l.dglb_coo_to_csr_workspace_bytes(n_rows, nnz)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    stream = _capi.enter(dev)
-    _capi.check(l.dglb_coo_to_csr(n_rows, nnz, _capi.ptr(row), _capi.ptr(col), _capi.ptr(indptr),
-                                  _capi.ptr(indices), _capi.ptr(data), _capi.ptr(ws), ws_bytes, stream),
-                "dglb_coo_to_csr")
+    o = _capi.ops()
+    indptr, indices, data = _capi.call(o.coo_to_csr, row.contiguous(), col.contiguous(), int(n_rows))
     if row_sorted is None:
-        flag = torch.empty(1, dtype=torch.int32, device=dev)
-        stream = _capi.enter(dev)
-        _capi.check(l.dglb_is_identity_perm(nnz, _capi.ptr(data), _capi.ptr(flag), stream), "dglb_is_identity_perm")
-        identity = bool(flag.item())
+        identity = bool(_capi.call(o.is_identity_perm, data).item())
     else:
         identity = bool(row_sorted)
     return CSRView(n_rows, n_cols, indptr, indices, None if identity else data)

@@ -25,21 +25,12 @@ def _hub_threshold(width, row_cta=False):
     one-CTA-per-row path of edge_softmax and the fused GAT kernels."""
     if HUB_THRESHOLD is not None:
         return int(HUB_THRESHOLD)
-    if row_cta:
-        return _capi.lib().dglb_default_row_hub_threshold(int(width))
-    return _capi.lib().dglb_default_hub_threshold(int(width))
+    return _capi.ops().default_hub_threshold(1 if row_cta else 0, int(width))
 
 
-def _hub_arg(info, dev=None, out_len=0, with_args=False):
-    """(ctypes pointer or None, objects to keep alive, extra launches) for a HubInfo."""
-    if info is None:
-        return None, None, 0
-    ws = None
-    if out_len:
-        nbytes = _capi.lib().dglb_hub_workspace_bytes(info.n_seg, int(out_len), 1 if with_args else 0)
-        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
-    st = info.struct(ws)
-    return ctypes.byref(st), (st, ws), (2 if out_len else 1)
+def _hub_pack(info):
+    """(hub arguments of an extension op, extra launches the hub path adds)."""
+    return (_capi.NO_HUB, 0) if info is None else (info.pack(), 1)
 
 
 # Staged edge order (include/dglb200.h, dglb_edge_stage_plan): on graphs whose CSC / CSR carries a non-trivial edge-id
@@ -67,15 +58,9 @@ def _stage_plan(view, row_floats, max_floats=None):
 
 
 def _stage_move(plan, t, to_staged):
-    """Edge-id order -> staged order (to_staged) or back, for a contiguous float32 per-edge tensor (E, ...)."""
-    out = torch.empty_like(t)
-    n = t.shape[0]
-    row_bytes = (t.numel() // n) * t.element_size()
-    stream = _capi.enter(t.device)
-    _capi.check(_capi.lib().dglb_edge_stage(1 if to_staged else 0, n, row_bytes, _capi.ptr(plan[0]), _capi.ptr(t),
-                                            _capi.ptr(out), stream), "dglb_edge_stage")
+    """Edge-id order -> staged order (to_staged) or back, for a contiguous per-edge tensor (E, ...)."""
     _capi.count_launch(1)
-    return out
+    return _capi.call(_capi.ops().edge_stage, plan[0], t, bool(to_staged))
 
 
 def infer_broadcast_shape(op, shp1, shp2):
@@ -110,7 +95,7 @@ def _shapes_for_abi(op, lhs, rhs):
     rs = (1,) * (n - len(rs)) + rs
     if n > 5:
         raise DGLError("feature tensors with more than 5 trailing dims are not supported")
-    return n, _capi.shape_arr(ls), _capi.shape_arr(rs)
+    return n, list(ls), list(rs)
 
 
 def _check_float32(*ts):
@@ -198,31 +183,24 @@ def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None, zero_inf=False):
             arg_e = torch.zeros(out_shape, dtype=gidx.idtype, device=dev) if use_e else None
     else:
         csc = gidx.csc()
-        v = out if out is not None else torch.empty(out_shape, dtype=ref.dtype, device=dev)  # every row is written
-        if use_cmp:
-            arg_u = torch.empty(out_shape, dtype=torch.int32, device=dev) if use_u else None
-            arg_e = torch.empty(out_shape, dtype=torch.int32, device=dev) if use_e else None
         out_len = 1
-        for s in feat_shape:
-            out_len *= s
-        l = _capi.lib()
-        thr = _hub_threshold(out_len)
-        hub, _keep, hub_launches = _hub_arg(csc.hubs(thr), dev, out_len, use_cmp)
+        for s_ in feat_shape:
+            out_len *= s_
+        hub, hub_launches = _hub_pack(csc.hubs(_hub_threshold(out_len)))
+        if hub_launches:
+            hub_launches = 2          # segment kernel + combine kernel
         ndim, ls, rs = _shapes_for_abi(op, u, e)
         eids = csc.eids
         if use_e and not use_cmp and dtype == _capi.F32:   # max / min record eids as arg_e: they need the real ids
             plan = _stage_plan(csc, e.numel() // max(e.shape[0], 1))
             if plan is not None:
                 e, eids = _stage_move(plan, e, True), plan[1]
-        stream = _capi.enter(dev)
-        rc = l.dglb_gspmm_csr(_capi.OPS[op], _capi.REDUCERS[reduce_op], dtype,
-                              csc.n_rows, csc.n_cols, csc.nnz,
-                              _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(eids),
-                              _capi.ptr(u), _capi.ptr(e), ndim, ls, rs,
-                              _capi.ptr(v), _capi.ptr(arg_u), _capi.ptr(arg_e), _capi.ptr(row_scale),
-                              (1 if out is not None else 0) | (2 if (zero_inf and use_cmp) else 0), hub, stream)
-        _capi.check(rc, "dglb_gspmm_csr")
+        flags = (1 if out is not None else 0) | (2 if (zero_inf and use_cmp) else 0)
+        v, arg_u, arg_e = _capi.call(_capi.ops().gspmm, csc.indptr, csc.indices, eids, csc.n_cols, _capi.OPS[op],
+                                     _capi.REDUCERS[reduce_op], u, e, list(feat_shape), ls, rs, row_scale, out, flags, *hub)
         _capi.count_launch(1 + hub_launches)
+        arg_u = arg_u if (use_cmp and use_u) else None
+        arg_e = arg_e if (use_cmp and use_e) else None
         if use_cmp and gidx.idtype != torch.int32:
             arg_u = arg_u.to(gidx.idtype) if arg_u is not None else None
             arg_e = arg_e.to(gidx.idtype) if arg_e is not None else None
@@ -276,9 +254,12 @@ def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
         pad = 8 - lhs.shape[1] % 8  # zero columns do not change the dot product; 128-bit loads instead of 32-bit
         return _gsddmm(gidx, op, torch.nn.functional.pad(lhs, (0, pad)), torch.nn.functional.pad(rhs, (0, pad)),
                        lhs_target, rhs_target)
-    out = torch.empty((gidx.n_edges,) + tuple(feat_shape), dtype=ref.dtype, device=dev)
-    if gidx.n_edges > 0 and out.numel() > 0:
-        l = _capi.lib()
+    out = None
+    out_numel = gidx.n_edges
+    for s_ in feat_shape:
+        out_numel *= s_
+    if gidx.n_edges > 0 and out_numel > 0:
+        o = _capi.ops()
         ndim, ls, rs = _shapes_for_abi(op, lhs, rhs)
         lt, rt = _TARGET[lhs_target], _TARGET[rhs_target]
         fmts = gidx.formats()
@@ -286,55 +267,47 @@ def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
         if use_csr:
             csc = gidx.csc()
             width = 1
-            for s in ref.shape[1:]:
-                width *= s
-            thr = _hub_threshold(width)
-            hub, _keep, hub_launches = _hub_arg(csc.hubs(thr))
+            for s_ in ref.shape[1:]:
+                width *= s_
+            hub, hub_launches = _hub_pack(csc.hubs(_hub_threshold(width)))
             # narrow results (u_dot_v, u_add_v on (N,H,1) scores) on a shuffled graph: the kernel writes them in
             # staged order (stores stay inside a 32 K-slot window), one pass then puts them in edge-id order
             plan = None
             if lhs_target == "u" and rhs_target == "v" and dtype == _capi.F32:
-                plan = _stage_plan(csc, out.numel() // gidx.n_edges)
-            dest = torch.empty_like(out) if plan is not None else out
-            stream = _capi.enter(dev)
-            rc = l.dglb_gsddmm_csr(_capi.OPS[op], dtype, lt, rt, csc.n_rows, csc.n_cols, csc.nnz,
-                                   _capi.ptr(csc.indptr), _capi.ptr(csc.indices),
-                                   _capi.ptr(plan[1] if plan is not None else csc.eids),
-                                   _capi.ptr(lhs), _capi.ptr(rhs), ndim, ls, rs, _capi.ptr(dest),
-                                   hub, stream)
-            _capi.check(rc, "dglb_gsddmm_csr")
+                plan = _stage_plan(csc, out_numel // gidx.n_edges)
+            out = _capi.call(o.gsddmm_csr, csc.indptr, csc.indices, plan[1] if plan is not None else csc.eids, csc.n_cols,
+                             _capi.OPS[op], lt, rt, lhs, rhs, list(feat_shape), ls, rs, *hub)
             _capi.count_launch(1 + hub_launches)
             if plan is not None:
-                out = _stage_move(plan, dest, False)
+                out = _stage_move(plan, out, False)
         else:
+            if dtype != _capi.F32:
+                raise DGLError("gsddmm_coo: only f32 is implemented")
             s32, d32 = gidx.coo32()
-            stream = _capi.enter(dev)
-            rc = l.dglb_gsddmm_coo(_capi.OPS[op], _capi.F32, lt, rt, gidx.n_src, gidx.n_dst, gidx.n_edges,
-                                   _capi.ptr(s32), _capi.ptr(d32), _capi.ptr(lhs), _capi.ptr(rhs), ndim, ls, rs,
-                                   _capi.ptr(out), stream)
-            _capi.check(rc, "dglb_gsddmm_coo")
+            out = _capi.call(o.gsddmm_coo, s32, d32, gidx.n_src, gidx.n_dst, _capi.OPS[op], lt, rt, lhs, rhs,
+                             list(feat_shape), ls, rs)
             _capi.count_launch(1)
+    if out is None:
+        out = torch.empty((gidx.n_edges,) + tuple(feat_shape), dtype=ref.dtype, device=dev)
     if (expand_lhs or not use_lhs) and (expand_rhs or not use_rhs):
         out = out.squeeze(-1)
     return out
 
 
-def _softmax_hub_arg(csc, heads, dev):
-    """Hub-row segments + workspace for edge_softmax: (ctypes pointer or None, keep-alive, launches)."""
-    thr = int(HUB_THRESHOLD) if HUB_THRESHOLD is not None else _capi.lib().dglb_default_softmax_hub_threshold(int(heads))
+def _softmax_hub(csc, heads):
+    """Hub-row segments for edge_softmax: (hub arguments without light_indptr, extra launches)."""
+    thr = int(HUB_THRESHOLD) if HUB_THRESHOLD is not None else _capi.ops().default_hub_threshold(2, int(heads))
     info = csc.hubs(thr)
     if info is None or heads > 32:
-        return None, None, 0
-    nbytes = _capi.lib().dglb_edge_softmax_workspace_bytes(info.n_seg, info.n_hub, int(heads))
-    ws = torch.empty(max(1, nbytes // 4), dtype=torch.float32, device=dev)
-    st = info.struct(ws)
-    return ctypes.byref(st), (st, ws), 3
+        return (None, None, None, []), 0
+    p = info.pack()
+    return (p[0], p[1], p[2], p[4]), 3
 
 
 def _edge_softmax_fwd(gidx, logits):
     """softmax over each destination's in-edges; logits (E, ...) in edge-id order."""
     _check_float32(logits)
-    dev = _capi.require_cuda(logits, gidx.src)
+    _capi.require_cuda(logits, gidx.src)
     if logits.shape[0] != gidx.n_edges:
         raise DGLError("edge_softmax: expect %d edge rows, got %d" % (gidx.n_edges, logits.shape[0]))
     logits = logits.contiguous()
@@ -342,17 +315,12 @@ def _edge_softmax_fwd(gidx, logits):
         return torch.empty_like(logits)
     heads = logits.numel() // gidx.n_edges
     csc = gidx.csc()
-    l = _capi.lib()
-    hub, _keep, hub_launches = _softmax_hub_arg(csc, heads, dev)
+    hub, hub_launches = _softmax_hub(csc, heads)
     plan = _stage_plan(csc, heads, STAGE_MAX_ROW_FLOATS_SOFTMAX)
     eids = csc.eids
     if plan is not None:
         logits, eids = _stage_move(plan, logits, True), plan[1]
-    out = torch.empty_like(logits)
-    stream = _capi.enter(dev)
-    rc = l.dglb_edge_softmax_fwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(eids),
-                                 _capi.ptr(logits), _capi.ptr(out), hub, stream)
-    _capi.check(rc, "dglb_edge_softmax_fwd")
+    out = _capi.call(_capi.ops().edge_softmax_fwd, csc.indptr, eids, logits, heads, *hub)
     _capi.count_launch(1 + hub_launches)
     if plan is not None:
         out = _stage_move(plan, out, False)
@@ -361,24 +329,19 @@ def _edge_softmax_fwd(gidx, logits):
 
 def _edge_softmax_bwd(gidx, out, grad_out):
     _check_float32(out, grad_out)
-    dev = _capi.require_cuda(out, grad_out, gidx.src)
+    _capi.require_cuda(out, grad_out, gidx.src)
     out = out.contiguous()
     grad_out = grad_out.contiguous()
-    grad = torch.empty_like(out)
     if gidx.n_edges == 0:
-        return grad
+        return torch.empty_like(out)
     heads = out.numel() // gidx.n_edges
     csc = gidx.csc()
-    l = _capi.lib()
-    hub, _keep, hub_launches = _softmax_hub_arg(csc, heads, dev)
+    hub, hub_launches = _softmax_hub(csc, heads)
     plan = _stage_plan(csc, heads, STAGE_MAX_ROW_FLOATS_SOFTMAX)
     eids = csc.eids
     if plan is not None:
         out, grad_out, eids = _stage_move(plan, out, True), _stage_move(plan, grad_out, True), plan[1]
-    stream = _capi.enter(dev)
-    rc = l.dglb_edge_softmax_bwd(_capi.F32, csc.n_rows, csc.nnz, heads, _capi.ptr(csc.indptr), _capi.ptr(eids),
-                                 _capi.ptr(out), _capi.ptr(grad_out), _capi.ptr(grad), hub, stream)
-    _capi.check(rc, "dglb_edge_softmax_bwd")
+    grad = _capi.call(_capi.ops().edge_softmax_bwd, csc.indptr, eids, out, grad_out, heads, *hub)
     _capi.count_launch(1 + hub_launches)
     if plan is not None:
         grad = _stage_move(plan, grad, False)
@@ -388,18 +351,13 @@ def _edge_softmax_bwd(gidx, out, grad_out):
 GAT_HUB_SEGMENTS = True  # False: one CTA per hub row (the pre-segmentation path, kept for comparison)
 
 
-def _gat_hub_arg(view, H, F, dev, launches):
-    """Hub rows of a CSRView for the fused GAT kernels: segment lists + workspace (segmented path)."""
+def _gat_hub(view, H, F, launches):
+    """Hub rows of a CSRView for the fused GAT kernels: (hub arguments without light_indptr, extra launches)."""
     info = view.hubs(_hub_threshold(H * F, row_cta=True))
     if info is None:
-        return None, None, 0
-    if not GAT_HUB_SEGMENTS:
-        st = info.struct(None)
-        return ctypes.byref(st), (st, None), 1
-    nbytes = _capi.lib().dglb_gat_hub_workspace_bytes(info.n_seg, int(H), int(F))
-    ws = torch.empty(max(4, nbytes // 4), dtype=torch.float32, device=dev)
-    st = info.struct(ws)
-    return ctypes.byref(st), (st, ws), launches
+        return (None, None, None, []), 0
+    p = info.pack()
+    return (p[0], p[1], p[2], p[4]), (launches if GAT_HUB_SEGMENTS else 1)
 
 
 def _gat_fwd(gidx, ft, el, er, slope, dropout_p, seed, want_scores=False, eids=None):
@@ -408,46 +366,30 @@ def _gat_fwd(gidx, ft, el, er, slope, dropout_p, seed, want_scores=False, eids=N
     the edge ids that key the dropout mask (row-partitioned graphs pass GLOBAL edge ids so the
     forward block and the backward block of different ranks regenerate the same mask)."""
     _check_float32(ft, el, er)
-    dev = _capi.require_cuda(ft, el, er, gidx.src)
+    _capi.require_cuda(ft, el, er, gidx.src)
     ft, el, er = ft.contiguous(), el.contiguous(), er.contiguous()
     H, F = ft.shape[1], ft.shape[2]
-    rst = torch.empty((gidx.n_dst, H, F), dtype=ft.dtype, device=dev)
-    row_max = torch.empty((gidx.n_dst, H), dtype=torch.float32, device=dev)
-    row_sum = torch.empty((gidx.n_dst, H), dtype=torch.float32, device=dev)
-    scores = torch.empty((gidx.n_edges, H), dtype=ft.dtype, device=dev) if want_scores else None
-    if gidx.n_dst == 0:
-        return rst, row_max, row_sum, scores
     csc = gidx.csc()
-    l = _capi.lib()
-    hub, _keep, hub_launches = _gat_hub_arg(csc, H, F, dev, 4)
-    stream = _capi.enter(dev)
-    rc = l.dglb_gat_fused_fwd(_capi.F32, csc.n_rows, csc.n_cols, csc.nnz, H, F, float(slope), float(dropout_p),
-                              int(seed), _capi.ptr(csc.indptr), _capi.ptr(csc.indices),
-                              _capi.ptr(eids if eids is not None else csc.eids),
-                              _capi.ptr(ft), _capi.ptr(el), _capi.ptr(er), _capi.ptr(rst), _capi.ptr(row_max),
-                              _capi.ptr(row_sum), _capi.ptr(scores), hub, stream)
-    _capi.check(rc, "dglb_gat_fused_fwd")
-    _capi.count_launch(1 + hub_launches)
-    return rst, row_max, row_sum, scores
+    hub, hub_launches = _gat_hub(csc, H, F, 4)
+    rst, row_max, row_sum, scores = _capi.call(
+        _capi.ops().gat_fwd, csc.indptr, csc.indices, eids if eids is not None else csc.eids, ft, el, er, float(slope),
+        float(dropout_p), int(seed), bool(want_scores), bool(GAT_HUB_SEGMENTS), *hub)
+    if gidx.n_dst:
+        _capi.count_launch(1 + hub_launches)
+    return rst, row_max, row_sum, (scores if want_scores else None)
 
 
 def _gat_bwd_dst(gidx, ft, el, er, row_max, row_sum, grad_rst, slope, dropout_p, seed, eids=None):
     """Destination pass of the fused GAT backward on gidx's CSC -> (row_pack (n_dst,H,4), grad_er)."""
-    dev = _capi.require_cuda(ft, el, er, grad_rst, gidx.src)
+    _capi.require_cuda(ft, el, er, grad_rst, gidx.src)
     grad_rst = grad_rst.contiguous()
     H, F = ft.shape[1], ft.shape[2]
-    row_pack = torch.empty((gidx.n_dst, H, 4), dtype=torch.float32, device=dev)  # {er, max, sum, s1}
-    grad_er = torch.empty((gidx.n_dst, H), dtype=ft.dtype, device=dev)
+    csc = gidx.csc()
+    hub, hub_launches = _gat_hub(csc, H, F, 2)
+    row_pack, grad_er = _capi.call(
+        _capi.ops().gat_bwd_dst, csc.indptr, csc.indices, eids if eids is not None else csc.eids, ft, el, er, row_max,
+        row_sum, grad_rst, float(slope), float(dropout_p), int(seed), bool(GAT_HUB_SEGMENTS), *hub)
     if gidx.n_dst:
-        csc = gidx.csc()
-        hub, _keep, hub_launches = _gat_hub_arg(csc, H, F, dev, 2)
-        stream = _capi.enter(dev)
-        rc = _capi.lib().dglb_gat_fused_bwd_dst(
-            _capi.F32, csc.n_rows, csc.n_cols, csc.nnz, H, F, float(slope), float(dropout_p), int(seed),
-            _capi.ptr(csc.indptr), _capi.ptr(csc.indices), _capi.ptr(eids if eids is not None else csc.eids),
-            _capi.ptr(ft), _capi.ptr(el), _capi.ptr(er), _capi.ptr(row_max), _capi.ptr(row_sum), _capi.ptr(grad_rst),
-            _capi.ptr(row_pack), _capi.ptr(grad_er), hub, stream)
-        _capi.check(rc, "dglb_gat_fused_bwd_dst")
         _capi.count_launch(1 + hub_launches)
     return row_pack, grad_er
 
@@ -456,20 +398,14 @@ def _gat_bwd_src(csr, ft, el, row_pack, grad_rst, slope, dropout_p, seed, eids=N
     """Source pass of the fused GAT backward on a CSRView whose rows are the source nodes and whose
     indices are destination ids -> (grad_ft (n_src,H,F), grad_el (n_src,H)).  row_pack / grad_rst are
     indexed by destination id."""
-    dev = _capi.require_cuda(ft, el, row_pack, grad_rst)
+    _capi.require_cuda(ft, el, row_pack, grad_rst)
     grad_rst = grad_rst.contiguous()
     H, F = ft.shape[1], ft.shape[2]
-    grad_ft = torch.empty_like(ft)
-    grad_el = torch.empty((csr.n_rows, H), dtype=ft.dtype, device=dev)
+    hub, hub_launches = _gat_hub(csr, H, F, 3)
+    grad_ft, grad_el = _capi.call(
+        _capi.ops().gat_bwd_src, csr.indptr, csr.indices, eids if eids is not None else csr.eids, csr.n_cols, ft, el,
+        row_pack, grad_rst, float(slope), float(dropout_p), int(seed), bool(GAT_HUB_SEGMENTS), *hub)
     if csr.n_rows:
-        hub, _keep, hub_launches = _gat_hub_arg(csr, H, F, dev, 3)
-        stream = _capi.enter(dev)
-        rc = _capi.lib().dglb_gat_fused_bwd_src(
-            _capi.F32, csr.n_rows, csr.n_cols, csr.nnz, H, F, float(slope), float(dropout_p), int(seed),
-            _capi.ptr(csr.indptr), _capi.ptr(csr.indices), _capi.ptr(eids if eids is not None else csr.eids),
-            _capi.ptr(ft), _capi.ptr(el), _capi.ptr(row_pack), _capi.ptr(grad_rst), _capi.ptr(grad_ft),
-            _capi.ptr(grad_el), hub, stream)
-        _capi.check(rc, "dglb_gat_fused_bwd_src")
         _capi.count_launch(1 + hub_launches)
     return grad_ft, grad_el
 

@@ -18,7 +18,8 @@ def _report():
     mod = sys.modules.get("dgl._capi")
     if mod is not None:
         sys.stderr.write("[dgl-b200] C-ABI compute calls: %d (library %s)\n"
-                         % (mod.launches(), mod.LIB_PATH if mod._lib is not None else "NOT LOADED"))
+                         % (mod.launches(), ("%s via %s" % (mod.LIB_PATH, mod.TORCH_LIB_PATH)) if mod._ops is not None
+                            else "NOT LOADED"))
         sys.stderr.flush()
 
 

@@ -86,3 +86,23 @@ def test_host_side_helpers_of_the_hub_paths(built_lib):
     assert rc == -1 and b"flag" in l.dglb_last_error()
     rc = l.dglb_gspmm_csr(4, 1, 0, 1, 1, 1, d, d, None, d, None, 1, shp, shp, d, None, None, None, 1, None, None)
     assert rc == -1 and b"accumulate" in l.dglb_last_error()
+
+
+def test_torch_extension_loads_and_fails_loudly_on_cpu_tensors():
+    """The PyTorch C++ extension (csrc_torch/ops.cpp, TORCH_LIBRARY "dglb200") is the product's only door into the
+    kernels: it must load, expose every op the Python layer calls, agree with the C library on the ABI version, and
+    refuse CPU tensors with an error (there is no CPU fallback to fall into)."""
+    import torch
+    from dgl import _capi
+    o = _capi.ops()
+    assert o.abi_version() == 2
+    for name in ("coo_to_csr", "csr_degrees", "is_identity_perm", "find_hub_rows", "edge_stage_plan", "edge_stage",
+                 "gspmm", "gsddmm_csr", "gsddmm_coo", "edge_softmax_fwd", "edge_softmax_bwd", "gat_fwd", "gat_bwd_dst",
+                 "gat_bwd_src", "default_hub_threshold"):
+        assert hasattr(o, name), name
+    assert o.default_hub_threshold(0, 602) == 256 and o.default_hub_threshold(1, 64) == 128
+    with pytest.raises(_capi.DGLError, match="CUDA-only"):
+        _capi.call(o.csr_degrees, torch.zeros(4, dtype=torch.int32))
+    ip = torch.tensor([0, 1, 2], dtype=torch.int32)
+    with pytest.raises(_capi.DGLError, match="CUDA-only"):
+        _capi.call(o.gspmm, ip, ip[:2], None, 2, 4, 0, torch.ones(2, 4), None, [4], [4], [4], None, None, 0, *_capi.NO_HUB)

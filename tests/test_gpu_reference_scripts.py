@@ -47,7 +47,7 @@ def run_script(rel, argv, scale, timeout=600):
     assert r.returncode == 0, "%s failed:\n%s\n%s" % (rel, r.stdout[-3000:], r.stderr[-3000:])
     m = re.search(r"C-ABI compute calls: (\d+) \(library (.*)\)", r.stderr)
     assert m, r.stderr[-2000:]
-    assert m.group(2).endswith("libdglb200.so"), m.group(2)
+    assert "libdglb200.so via " in m.group(2) and m.group(2).endswith("libdglb200_torch.so"), m.group(2)
     return r.stdout, int(m.group(1))
 
 
