@@ -329,8 +329,9 @@ int ring_rows(bool dot, int dtype, int64_t n_rows, int64_t n_cols, int64_t nnz, 
   // single process can A/B them (examples/ring_tune.py, tests/test_gpu_ring.py).
   const int esz = dtype == DGLB_BF16 ? 2 : 4;
   const int64_t row_bytes = D * esz;
-  // (bf16 u_dot_v at 1.2 KB rows is bound by the copy rate: 6.3 ms vs 4.1 ms on the padded register path)
-  const int min_bytes = env_int("DGLB_RING_MIN_BYTES", ((row_bytes % 16) && !(dot && dtype == DGLB_BF16)) ? 1024 : 2048);
+  // (measured with the short per-edge path: bf16 D = 602, 1 204-byte rows: gspmm 2.08 ms vs 4.43 ms on the padded register
+  //  path, u_dot_v 3.25 vs 4.08 ms; bf16 D = 1000, 2 000-byte aligned rows: 3.11 vs 3.92 ms, 3.37 vs 4.16 ms)
+  const int min_bytes = env_int("DGLB_RING_MIN_BYTES", (row_bytes % 16) ? 1024 : 1792);
   const int min_nnz = env_int("DGLB_RING_MIN_NNZ", 1 << 18);
   const int force_s = env_int("DGLB_RING_STAGES", 0);
   // Depth: throughput peaks at ~115-130 KB of rows in flight per SM and DROPS beyond it (D = 602: 3.9 ms at 48 rows in

@@ -138,12 +138,16 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0
     const int mmax = min(G, nmax - off);
     for (int t = 0; t < mmax; t += U) {
       int cc[U], ee[U];
+      float ww[RMODE == RMODE_SCALAR ? U : 1];
       StageVec<T, VEC> xv[U][CH];  // bf16 rows stay packed until consumed
       FVec<(VEC > 4 ? 4 : VEC)> wv[U][CH];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         cc[u] = USE_L ? __shfl_sync(FULL_MASK, my_c, t + u, G) : 0;
         ee[u] = (NEED_E && (RMODE != RMODE_SCALAR || TRACK_E)) ? __shfl_sync(FULL_MASK, my_e, t + u, G) : 0;
+        // scalar weights: every shuffle of the batch happens BEFORE the gathers are issued -- with the weight
+        // shuffles in the consume phase ptxas split the 8 gathers into 3 + 5 around them (SASS)
+        if constexpr (RMODE == RMODE_SCALAR) ww[u] = __shfl_sync(FULL_MASK, my_w, t + u, G);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -164,7 +168,7 @@ __device__ __forceinline__ void accumulate_range(const SpmmParams& p, int64_t j0
       for (int u = 0; u < U; ++u) {
         const bool valid = (t + u) < m;
         float ws = 0.f;
-        if constexpr (RMODE == RMODE_SCALAR) ws = __shfl_sync(FULL_MASK, my_w, t + u, G);
+        if constexpr (RMODE == RMODE_SCALAR) ws = ww[u];
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           if (valid && colv[c]) {

@@ -249,7 +249,7 @@ def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
         rhs = rhs.contiguous()
     feat_shape = infer_broadcast_shape(op, lhs.shape[1:] if use_lhs else (1,), rhs.shape[1:] if use_rhs else (1,))
     ref = lhs if use_lhs else rhs
-    ring = lhs is not None and lhs.dim() == 2 and lhs.shape[1] * 2 >= 2048 and lhs.shape[1] % 2 == 0 and gidx.n_edges >= (1 << 18)
+    ring = lhs is not None and lhs.dim() == 2 and lhs.shape[1] * 2 >= 1024 and lhs.shape[1] % 2 == 0 and gidx.n_edges >= (1 << 18)
     if dtype == _capi.BF16 and lhs.dim() == 2 and lhs.shape[1] >= 32 and lhs.shape[1] % 8 and not ring:
         pad = 8 - lhs.shape[1] % 8  # zero columns do not change the dot product; 128-bit loads instead of 32-bit
         return _gsddmm(gidx, op, torch.nn.functional.pad(lhs, (0, pad)), torch.nn.functional.pad(rhs, (0, pad)),

@@ -32,7 +32,7 @@ class SAGELayer(nn.Module):
     def __init__(self, in_feats, out_feats, aggr="mean", feat_drop=0.0, activation=None):
         super().__init__()
         self.aggr, self.activation = aggr, activation
-        self.lin_before_mp = SAGELayer.project_first and in_feats > out_feats
+        self.in_feats, self.out_feats = in_feats, out_feats
         self.feat_drop = nn.Dropout(feat_drop)
         self.fc_self = nn.Linear(in_feats, out_feats, bias=False)
         self.fc_neigh = nn.Linear(in_feats, out_feats)
@@ -45,8 +45,17 @@ class SAGELayer(nn.Module):
 
     def forward(self, graph, feat):
         h = self.feat_drop(feat)
-        if self.lin_before_mp:
-            z = torch.nn.functional.linear(h, self.fc_neigh.weight)
+        # project first when it shrinks the sparse work: with a trainable input both the forward and the backward
+        # aggregation narrow from `in` to `out`; with a constant input (first layer) the input-width backward
+        # aggregation would have been skipped anyway, so the projection has to more than halve the width to pay
+        # (products layer 1, 100 -> 64: 5.2 ms before vs 2.7 + 2.7 ms after; reddit layer 1, 602 -> 16: 3.9 vs 0.2 ms)
+        need = self.out_feats if h.requires_grad else 2 * self.out_feats
+        if SAGELayer.project_first and self.in_feats > need:
+            w = self.fc_neigh.weight
+            pad = (-self.out_feats) % 4      # keep the aggregated rows 16-byte aligned (47 classes -> 48 columns)
+            if pad:
+                w = torch.nn.functional.pad(w, (0, 0, 0, pad))
+            z = torch.nn.functional.linear(h, w)
             if hasattr(graph, "copy_u_sum"):
                 zn = graph.copy_u_sum(z, self.aggr)
             else:
@@ -54,6 +63,8 @@ class SAGELayer(nn.Module):
                 g.srcdata["h"] = z
                 g.update_all(fn.copy_src("h", "m"), fn.mean("m", "neigh") if self.aggr == "mean" else fn.sum("m", "neigh"))
                 zn = g.dstdata["neigh"]
+            if pad:
+                zn = zn[:, :self.out_feats]
             rst = self.fc_self(h) + zn + self.fc_neigh.bias
             return self.activation(rst) if self.activation is not None else rst
         if hasattr(graph, "copy_u_sum"):          # RowPartition: collective + local kernel

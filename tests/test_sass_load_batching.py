@@ -18,6 +18,9 @@ KERNELS = {  # mangled-name fragment -> minimum run of vector loads with no FP i
     "sddmm_dot_kernelILi4ELi1ELi4ELb1ELb0EfEE": 6,        # D=64
     "sddmm_dot_kernelILi4ELi2ELi5ELb1ELb0EfEE": 6,        # D=256
     "spmm_rows_kernelILi8ELi4ELi4ELi0ELi0E13__nv_bfloat16": 6,  # bf16 storage, D=608
+    # u_mul_e_sum with (E,1) weights, D=64: the weight shuffles are hoisted in front of the gathers; with them in
+    # the consume phase ptxas issued the batch as 3 + 5 gathers
+    "spmm_rows_kernelILi4ELi1ELi2ELi0ELi3EfEE": 7,
 }
 
 
