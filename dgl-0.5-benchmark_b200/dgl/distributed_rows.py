@@ -193,9 +193,9 @@ class RowPartition:
         """Switch the exchange to ring-ordered peer pulls through symmetric memory (CUDA + NCCL process group)."""
         assert self.chunks == 1, "the peer-to-peer exchange uses the one-slot-per-rank gather layout"
         self._p2p, self._p2p_group = {}, (group if group is not None else dist.group.WORLD)
-        # two copy streams: consecutive pulls alternate between them so one copy's start-up latency hides behind
-        # the other's transfer (28 pulls of 7-70 MB per step at 8 GPUs)
-        self._copy_streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        # ONE copy stream: measured at 8 GPUs (profiles/r02_p2p_copy_bench_n8.jsonl) a single in-order stream of pulls
+        # moves 70 MB shards at 609 GB/s per rank, two streams 562, four 371
+        self._copy_streams = [torch.cuda.Stream()]
         return self
 
     @property
@@ -215,8 +215,9 @@ class RowPartition:
             self._p2p[key] = (t, hdl, views)
         return self._p2p[key]
 
-    def p2p_gather(self, xs):
-        """Start the exchange of a list of local row tensors.  Returns [(buffer, events)] per operand: the padded
+    def p2p_gather(self, xs, order="operand"):
+        """Start the exchange of a list of local row tensors (order: "operand" = all shards of xs[0], then xs[1], ...;
+        "group" = peer group by peer group across the operands).  Returns [(buffer, events)] per operand: the padded
         gather buffer (the local shard is in place in stream order) and events[k], k = 1..P-1, which fire once the
         shard of rank (rank + k) mod P has landed.  Two device-side barriers per call (not per operand): peers have
         finished reading what the symmetric buffers held before / every rank has published its new rows."""
@@ -247,19 +248,22 @@ class RowPartition:
         for st in self._copy_streams:
             st.wait_event(ready)
         i = 0
-        for steps in groups:
-            for oi, (x, (t, _, views), gbuf) in enumerate(zip(xs, slots, gbufs)):
-                for k in steps:
-                    peer = (self.rank + k) % P
-                    n_peer = self.sizes[peer]
-                    st = self._copy_streams[i % len(self._copy_streams)]
-                    i += 1
-                    with torch.cuda.stream(st):
-                        if n_peer:
-                            gbuf[peer * cr: peer * cr + n_peer].copy_(views[peer][:n_peer], non_blocking=True)
-                        ev = torch.cuda.Event()
-                        ev.record(st)
-                    all_events[oi][k] = ev
+        if order == "group":
+            plan = [(oi, k) for steps in groups for oi in range(len(xs)) for k in steps]
+        else:
+            plan = [(oi, k) for oi in range(len(xs)) for steps in groups for k in steps]
+        for oi, k in plan:
+            views, gbuf = slots[oi][2], gbufs[oi]
+            peer = (self.rank + k) % P
+            n_peer = self.sizes[peer]
+            st = self._copy_streams[i % len(self._copy_streams)]
+            i += 1
+            with torch.cuda.stream(st):
+                if n_peer:
+                    gbuf[peer * cr: peer * cr + n_peer].copy_(views[peer][:n_peer], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            all_events[oi][k] = ev
         for gbuf in gbufs:
             for st in self._copy_streams:
                 gbuf.record_stream(st)

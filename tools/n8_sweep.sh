@@ -7,13 +7,5 @@ try:
 except Exception as ex: print("parse failed", ex)
 PY
 }
-run g_default --no-extras
-run g_1_3_4 --no-extras --peer-groups 1,3,4
-run g_1_7 --no-extras --peer-groups 1,7
-run g_1_1_1_1_1_1_1_1 --no-extras --peer-groups 1,1,1,1,1,1,1,1
-for ex in p2p nccl; do DGLB_EXCHANGE=$ex python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 epoch_bench.py --configs products_sage,products_gat --epochs 9 2>/dev/null | python -c "
-import sys, json
-for l in sys.stdin:
-    try: d=json.loads(l); print('$ex', d['config'], round(d['epoch_s']*1e3,2), 'ms', d['loss_first'], d['loss_last'])
-    except Exception: pass
-" | tee -a gpurun_out/epochs_n8.txt; done
+run wf_default --no-extras
+run wf_1_2_2_2_1 --no-extras --peer-groups 1,2,2,2,1
