@@ -19,7 +19,7 @@ class CSRView:
     """indptr / indices / eids (None == identity) over `n_rows` rows, all int32 device tensors,
     plus per-threshold hub-row lists (caller-owned metadata of the C-ABI)."""
 
-    __slots__ = ("n_rows", "n_cols", "indptr", "indices", "eids", "_hubs", "_deg", "_deg_f", "_stage")
+    __slots__ = ("n_rows", "n_cols", "indptr", "indices", "eids", "_hubs", "_deg", "_deg_f", "_stage", "max_deg")
 
     LOG2_STAGE_BUCKET = 15  # staged edge order: slots are shuffled inside windows of 32 K CSR positions
 
@@ -30,6 +30,7 @@ class CSRView:
         self._deg = None
         self._deg_f = None
         self._stage = None
+        self.max_deg = None   # largest row length when it is known from the host side (graphs built from CPU tensors)
 
     def stage_plan(self):
         """(stage_pos by edge id, slot by CSR position) of the staged edge order (include/dglb200.h,
@@ -61,7 +62,9 @@ class CSRView:
         if threshold in self._hubs:
             return self._hubs[threshold]
         info = None
-        if self.nnz > threshold:  # otherwise no row can exceed it: no kernel, no sync (small batched graphs)
+        if self.max_deg is not None and self.max_deg <= threshold:
+            pass                  # known from the host side: no hub rows, no kernel, no device sync (batched molecules)
+        elif self.nnz > threshold:  # otherwise no row can exceed it: no kernel, no sync (small batched graphs)
             dev = self.indptr.device
             cap = max(1, min(self.n_rows, self.nnz // max(threshold, 1) + 1))
             rows, n_hub_t = _capi.call(_capi.ops().find_hub_rows, self.indptr, int(threshold), cap)
@@ -111,7 +114,7 @@ class HubInfo:
         return st
 
 
-def build_csr(n_rows, n_cols, row, col, row_sorted=None):
+def build_csr(n_rows, n_cols, row, col, row_sorted=None, max_deg=None):
     """Stable sort of (row, col) by row on the device -> CSRView.  `row_sorted` (True/False/None):
     whether `row` is already non-decreasing, i.e. the edge-id permutation is the identity; when it is
     known from the host side (graphs created from CPU tensors) the device check and its sync are skipped."""
@@ -122,7 +125,9 @@ def build_csr(n_rows, n_cols, row, col, row_sorted=None):
         identity = bool(_capi.call(o.is_identity_perm, data).item())
     else:
         identity = bool(row_sorted)
-    return CSRView(n_rows, n_cols, indptr, indices, None if identity else data)
+    view = CSRView(n_rows, n_cols, indptr, indices, None if identity else data)
+    view.max_deg = max_deg
+    return view
 
 
 class GraphIndex:
@@ -135,13 +140,18 @@ class GraphIndex:
         # caches shared with the reversed view
         self._c = _shared if _shared is not None else {"csc": None, "csr": None, "coo32": None,
                                                          "formats": {"coo", "csr", "csc"},
-                                                         "dst_sorted": None, "src_sorted": None}
+                                                         "dst_sorted": None, "src_sorted": None,
+                                                         "max_in_deg": None, "max_out_deg": None}
         self._rev = False
         if _shared is None and src.device.type == "cpu" and src.numel() <= (1 << 22):
             # cheap on the host, saves a device round trip per graph (matters for batched small graphs)
             n = src.numel()
             self._c["dst_sorted"] = bool(n < 2 or bool((dst[1:] >= dst[:-1]).all()))
             self._c["src_sorted"] = bool(n < 2 or bool((src[1:] >= src[:-1]).all()))
+            # largest in / out degree: lets the kernels' hub-row detection (a device kernel + a sync per new graph)
+            # be skipped for batched small graphs, whose rows are a handful of edges long
+            self._c["max_in_deg"] = int(torch.bincount(dst.long(), minlength=1).max()) if n else 0
+            self._c["max_out_deg"] = int(torch.bincount(src.long(), minlength=1).max()) if n else 0
 
     # ---- basic properties
     @property
@@ -184,6 +194,8 @@ class GraphIndex:
         g._c["formats"] = set(self._c["formats"])
         a, b = self._c["dst_sorted"], self._c["src_sorted"]
         g._c["dst_sorted"], g._c["src_sorted"] = (a, b) if not self._rev else (b, a)
+        a, b = self._c["max_in_deg"], self._c["max_out_deg"]
+        g._c["max_in_deg"], g._c["max_out_deg"] = (a, b) if not self._rev else (b, a)
 
     def formats(self):
         return set(self._c["formats"])
@@ -212,9 +224,9 @@ class GraphIndex:
             n_s = self.n_src if not self._rev else self.n_dst
             n_d = self.n_dst if not self._rev else self.n_src
             if key == "csc":
-                self._c[key] = build_csr(n_d, n_s, d, s, self._c["dst_sorted"])
+                self._c[key] = build_csr(n_d, n_s, d, s, self._c["dst_sorted"], self._c["max_in_deg"])
             else:
-                self._c[key] = build_csr(n_s, n_d, s, d, self._c["src_sorted"])
+                self._c[key] = build_csr(n_s, n_d, s, d, self._c["src_sorted"], self._c["max_out_deg"])
         return self._c[key]
 
     def csc(self):
