@@ -109,9 +109,9 @@ def ncu_traffic():
     if not os.path.exists(path):
         return None, "no committed ncu capture"
     rec = json.load(open(path))["gspmm_copy_u_sum_d602"]
-    src = os.path.join(PKG, "csrc", "spmm.cu")
+    src = os.path.join(PKG, "csrc", "ring.cu")
     sha = hashlib.sha256(open(src, "rb").read()).hexdigest()[:16]
-    state = "current" if sha == rec.get("spmm_cu_sha256_16") else "stale: csrc/spmm.cu changed since the capture"
+    state = "current" if sha == rec.get("ring_cu_sha256_16") else "stale: csrc/ring.cu changed since the capture"
     return int(rec["dram_bytes_per_launch"]), "%s (%s)" % (rec["from"], state)
 
 
@@ -503,11 +503,14 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "roofline": {"bound": "hbm", "kernel": "spmm_rows_kernel<VEC=2,CH=4,copy_lhs,sum> (gspmm copy_u_sum, D=602)",
+            "roofline": {"bound": "hbm", "kernel": "ring_kernel<float,VEC=2,NCH=10,DOT=false> (gspmm copy_u_sum, D=602: whole-row "
+                                                   "cp.async.bulk into a per-warp shared-memory ring; hub rows, if any, in spmm_hub_kernel)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": kb,
-                         "note": ("single launch timed by its own CUDA-event pair" if world == 1 else
+                         "note": ("single launch timed by its own CUDA-event pair; the peak is a measured COPY bandwidth "
+                                  "(read+write): a read-dominated gather can exceed it -- ncu: 25.3 GB of DRAM traffic per "
+                                  "launch = 6.5 TB/s = 0.80 of the DRAM pin rate" if world == 1 else
                                   "N>1: the event pair spans the chunk-by-chunk gather waits + aggregation of this rank's rows")},
             "e2e": {"value": e2e_val, "unit": "GB/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},

@@ -164,6 +164,9 @@ __global__ void __launch_bounds__(kRingThreads, 3) ring_kernel(const RingParams 
   EdgeCursor pc;  // producer cursor
   pc.row = r0 - 1; pc.row_end = r1; pc.pos = pc.end = 0;
   pc.settle(p);
+  // the source id of the cursor's edge is fetched one step ahead (ncu: the producer's index load was the kernel's top
+  // stall -- long scoreboard 10.8 per issue -- because every copy request waited for its own index)
+  int pc_col = pc.valid ? __ldg(p.indices + pc.pos) : 0;
   int in_flight = 0;            // copies requested and not yet consumed
   int pslot = 0, cslot = 0;     // next slot to fill / to consume
   uint32_t cphase = 0;          // parity the consumer waits for on cslot
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(kRingThreads, 3) ring_kernel(const RingParams 
 
   auto fill = [&]() {
     while (pc.valid && in_flight < S) {
-      const int c = __ldg(p.indices + pc.pos);
+      const int c = pc_col;
       const unsigned char* g = p.X + (int64_t)c * row_bytes;
       const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15);
       if (c == last_col && last_unsafe) {   // copy it by hand (warp-uniform branch)
@@ -194,6 +197,7 @@ __global__ void __launch_bounds__(kRingThreads, 3) ring_kernel(const RingParams 
       ++in_flight;
       if (++pslot == S) pslot = 0;
       if (++pc.pos >= pc.end) pc.settle(p);
+      if (pc.valid) pc_col = __ldg(p.indices + pc.pos);
     }
   };
 
