@@ -186,7 +186,11 @@ def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None, zero_inf=False):
         out_len = 1
         for s_ in feat_shape:
             out_len *= s_
-        hub, hub_launches = _hub_pack(csc.hubs(_hub_threshold(out_len)))
+        # relation broadcast (N,1,D) x (E,R,1) -> (N,R,D), R in {2,4,8}: the batched RGCN kernel gathers a neighbour row
+        # once for all R relations; it has no split-row path, so no hub rows are handed to it
+        rel = (op == "mul" and not use_cmp and out is None and dtype == _capi.F32 and u.dim() == 3 and e.dim() == 3
+               and u.shape[1] == 1 and e.shape[2] == 1 and e.shape[1] in (2, 4, 8) and 1 < u.shape[2] <= 128)
+        hub, hub_launches = (_capi.NO_HUB, 0) if rel else _hub_pack(csc.hubs(_hub_threshold(out_len)))
         if hub_launches:
             hub_launches = 2          # segment kernel + combine kernel
         ndim, ls, rs = _shapes_for_abi(op, u, e)

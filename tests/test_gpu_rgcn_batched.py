@@ -144,3 +144,39 @@ def test_batched_coo_copy_u_sum_and_readout(oracle, cuda):
     xs = np.split(n(bg.ndata["x"]).astype(np.float64), np.cumsum(sizes)[:-1])
     want = np.stack([a.mean(0) for a in xs])
     np.testing.assert_allclose(pooled, want, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("R", [2, 4, 8])
+@pytest.mark.parametrize("D", [4, 32, 100])
+@pytest.mark.parametrize("order", ["shuffled", "dst_sorted"])
+def test_rgcn_batched_relations_one_launch(oracle, cuda, R, D, order):
+    """All R relations of the RGCN layer in ONE gspmm: lhs (N,1,D) x rhs (E,R,1) -> (N,R,D) (relation-broadcast kernel:
+    a neighbour row is gathered once for all relations).  Every relation's slice is bit-identical to the per-relation
+    u_mul_e_{sum,mean} the unchanged script computes (main_dgl_proteins_rgcn_for.py:50-53), and to the oracle; the
+    gradient w.r.t. the node features equals the sum of the per-relation gradients."""
+    from dgl import sparse as K
+    N, E = 500, 40000                                      # in-degree ~80: long rows, as on ogbn-proteins
+    og, g, src, dst = graphs(oracle, N, N, E, seed=23, order=order)
+    old_thr, K.HUB_THRESHOLD = K.HUB_THRESHOLD, 1 << 30    # per-relation reference without split rows: sequential sums
+    rng = np.random.default_rng(23)
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    W = rng.random((E, R), dtype=np.float32)
+    for red in ("sum", "mean"):
+        xt = t(X).requires_grad_(True)
+        launches0 = dgl._capi.launches()
+        out = dgl.ops.gspmm(g, "mul", red, xt.unsqueeze(1), t(W).unsqueeze(-1))
+        assert dgl._capi.launches() - launches0 == 1
+        assert out.shape == (N, R, D)
+        want = oracle.gspmm(og, "mul", red, X[:, None, :], W[:, :, None])
+        assert np.array_equal(n(out), want)
+        gout = rng.standard_normal((N, R, D)).astype(np.float32)
+        out.backward(t(gout))
+        ref_grad = torch.zeros(N, D, device="cuda")
+        for r in range(R):
+            xr = t(X).requires_grad_(True)
+            o_r = dgl.ops.gspmm(g, "mul", red, xr, t(np.ascontiguousarray(W[:, r:r + 1])))
+            assert torch.equal(o_r, out[:, r, :].detach())                       # per-relation result, bit for bit
+            o_r.backward(t(np.ascontiguousarray(gout[:, r, :])))
+            ref_grad += xr.grad
+        np.testing.assert_allclose(n(xt.grad), n(ref_grad), rtol=1e-4, atol=1e-4)
+    K.HUB_THRESHOLD = old_thr
