@@ -353,4 +353,51 @@ int dglb_gat_fused_bwd_src(int dtype, int64_t n_src, int64_t n_dst, int64_t nnz,
   return gat_fused_f32(2, p, n_heads, head_dim, dropout_p, seed, hub, static_cast<cudaStream_t>(stream));
 }
 
+int dglb_gcn_msg_sum_fwd(int64_t n_dst, int64_t n_src, int64_t nnz, int64_t feat_len, const int32_t* indptr,
+                         const int32_t* indices, const int32_t* eids, const float* x, const float* w, const float* c_src,
+                         const float* c_dst, float* out, void* stream) {
+  DGLB_CHECK_ARG(n_dst >= 0 && n_src >= 0 && nnz >= 0 && feat_len >= 0, "gcn_msg_sum_fwd: negative size");
+  DGLB_CHECK_ARG(n_dst == 0 || (indptr && c_dst && (out || feat_len == 0)), "gcn_msg_sum_fwd: null dst data");
+  DGLB_CHECK_ARG(nnz == 0 || (indices && x && w && c_src), "gcn_msg_sum_fwd: null operand with nnz > 0");
+  return gcn_msg_sum_fwd(n_dst, feat_len, indptr, indices, eids, x, w, c_src, c_dst, out, static_cast<cudaStream_t>(stream));
+}
+
+int dglb_gcn_msg_sum_bwd(int64_t n_src, int64_t n_dst, int64_t nnz, int64_t feat_len, const int32_t* indptr_csr,
+                         const int32_t* indices_csr, const int32_t* eids_csr, const float* x, const float* w,
+                         const float* c_src, const float* c_dst, const float* grad_out, float* grad_x, float* grad_w,
+                         void* stream) {
+  DGLB_CHECK_ARG(n_dst >= 0 && n_src >= 0 && nnz >= 0 && feat_len >= 0, "gcn_msg_sum_bwd: negative size");
+  DGLB_CHECK_ARG(n_src == 0 || (indptr_csr && c_src && x && (grad_x || feat_len == 0)), "gcn_msg_sum_bwd: null src data");
+  DGLB_CHECK_ARG(nnz == 0 || (indices_csr && w && c_dst && grad_out && grad_w), "gcn_msg_sum_bwd: null operand with nnz > 0");
+  return gcn_msg_sum_bwd(n_src, feat_len, indptr_csr, indices_csr, eids_csr, x, w, c_src, c_dst, grad_out, grad_x, grad_w,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int dglb_batch_offsets(int64_t n_sel, const int32_t* graph_ids, const int32_t* node_ptr, const int32_t* edge_ptr,
+                       int32_t* out_node_ptr, int32_t* out_edge_ptr, int64_t n_nodes_pad, int64_t n_edges_pad,
+                       int32_t* status, void* stream) {
+  DGLB_CHECK_ARG(n_sel >= 0 && n_sel < (1LL << 31) && n_nodes_pad >= 0 && n_nodes_pad < (1LL << 31) && n_edges_pad >= 0 &&
+                     n_edges_pad < (1LL << 31), "batch_offsets: sizes must fit int32");
+  DGLB_CHECK_ARG(out_node_ptr && out_edge_ptr && node_ptr && edge_ptr && (graph_ids || n_sel == 0),
+                 "batch_offsets: null array");
+  return batch_offsets(n_sel, graph_ids, node_ptr, edge_ptr, out_node_ptr, out_edge_ptr, n_nodes_pad, n_edges_pad, status,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int dglb_batch_gather(const dglb_batch_io_t* io, void* stream) {
+  DGLB_CHECK_ARG(io != nullptr, "batch_gather: io is null");
+  DGLB_CHECK_ARG(io->n_sel >= 0 && io->n_nodes_pad >= 0 && io->n_edges_pad >= 0, "batch_gather: negative size");
+  DGLB_CHECK_ARG(io->node_ptr && io->edge_ptr && io->out_node_ptr && io->out_edge_ptr && (io->graph_ids || io->n_sel == 0),
+                 "batch_gather: null selection / offset array");
+  DGLB_CHECK_ARG(!(io->src || io->dst) || (io->u_src && io->u_dst), "batch_gather: COO outputs need the union COO");
+  DGLB_CHECK_ARG(!(io->csc_indptr || io->csc_indices) || (io->u_csc_indptr && io->u_csc_indices),
+                 "batch_gather: CSC outputs need the union CSC");
+  DGLB_CHECK_ARG(!(io->csr_indptr || io->csr_indices) || (io->u_csr_indptr && io->u_csr_indices),
+                 "batch_gather: CSR outputs need the union CSR");
+  DGLB_CHECK_ARG((io->csc_indices == nullptr) == (io->csc_eids == nullptr) &&
+                     (io->csr_indices == nullptr) == (io->csr_eids == nullptr),
+                 "batch_gather: indices and eids outputs come in pairs");
+  return batch_gather(*io, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

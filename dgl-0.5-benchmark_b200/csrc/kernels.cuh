@@ -98,4 +98,16 @@ int gat_fused_f32(int which, GatParams& p, int64_t H, int64_t F, float dropout_p
                   const dglb_hub_t* hub, cudaStream_t stream);
 size_t gat_hub_workspace_bytes(int64_t n_seg, int64_t H, int64_t F);
 
+// small_graph.cu
+int gcn_msg_sum_fwd(int64_t n_dst, int64_t D, const int32_t* indptr, const int32_t* indices, const int32_t* eids,
+                    const float* x, const float* w, const float* c_src, const float* c_dst, float* out,
+                    cudaStream_t stream);
+int gcn_msg_sum_bwd(int64_t n_src, int64_t D, const int32_t* indptr, const int32_t* indices, const int32_t* eids,
+                    const float* x, const float* w, const float* c_src, const float* c_dst, const float* gout, float* gx,
+                    float* gw, cudaStream_t stream);
+int batch_offsets(int64_t n_sel, const int32_t* graph_ids, const int32_t* node_ptr, const int32_t* edge_ptr,
+                  int32_t* out_node_ptr, int32_t* out_edge_ptr, int64_t n_nodes_pad, int64_t n_edges_pad, int32_t* status,
+                  cudaStream_t stream);
+int batch_gather(const dglb_batch_io_t& io, cudaStream_t stream);
+
 }  // namespace dglb

@@ -356,6 +356,92 @@ std::tuple<Tensor, Tensor> gat_bwd_src(const Tensor& indptr, const Tensor& indic
   return {grad_ft, grad_el};
 }
 
+// ------------------------------------------------------------------ batched small graphs
+Tensor gcn_msg_sum_fwd(const Tensor& indptr, const Tensor& indices, const OptTensor& eids, const Tensor& x, const Tensor& w,
+                       const Tensor& c_src, const Tensor& c_dst) {
+  need_cuda(x, "x"); need_cuda(w, "w"); need_cuda(c_src, "c_src"); need_cuda(c_dst, "c_dst");
+  TORCH_CHECK(x.scalar_type() == at::kFloat && w.scalar_type() == at::kFloat && c_src.scalar_type() == at::kFloat &&
+                  c_dst.scalar_type() == at::kFloat, "dgl-b200 kernels compute in float32");
+  const int64_t n_dst = indptr.numel() - 1, nnz = indices.numel(), n_src = x.size(0);
+  TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && w.size(0) == nnz && w.size(1) == x.size(1),
+              "gcn_msg_sum: expect x (n_src, D) and w (n_edges, D); got ", x.sizes(), " and ", w.sizes());
+  TORCH_CHECK(c_src.numel() == n_src && c_dst.numel() == n_dst, "gcn_msg_sum: norm vectors must have one entry per node");
+  Tensor out = at::empty({n_dst, x.size(1)}, x.options());
+  if (out.numel() == 0) return out;
+  Entered en(x);
+  check_status(dglb_gcn_msg_sum_fwd(n_dst, n_src, nnz, x.size(1), i32(indptr, "indptr"), i32(indices, "indices"),
+                                    i32_opt(eids, "eids"), x.data_ptr<float>(), w.data_ptr<float>(), c_src.data_ptr<float>(),
+                                    c_dst.data_ptr<float>(), out.data_ptr<float>(), en.stream), "dglb_gcn_msg_sum_fwd");
+  return out;
+}
+
+// CSR over the source nodes; zero_grad_w: the graph has edge slots that no CSR row covers (fixed-size padded batch)
+std::tuple<Tensor, Tensor> gcn_msg_sum_bwd(const Tensor& indptr_csr, const Tensor& indices_csr, const OptTensor& eids_csr,
+                                           const Tensor& x, const Tensor& w, const Tensor& c_src, const Tensor& c_dst,
+                                           const Tensor& grad_out, bool zero_grad_w) {
+  need_cuda(x, "x"); need_cuda(w, "w"); need_cuda(c_src, "c_src"); need_cuda(c_dst, "c_dst"); need_cuda(grad_out, "grad_out");
+  TORCH_CHECK(grad_out.scalar_type() == at::kFloat && x.scalar_type() == at::kFloat && w.scalar_type() == at::kFloat,
+              "dgl-b200 kernels compute in float32");
+  const int64_t n_src = indptr_csr.numel() - 1, nnz = indices_csr.numel(), n_dst = grad_out.size(0);
+  TORCH_CHECK(x.size(0) == n_src && w.size(0) == nnz && grad_out.size(1) == x.size(1) && c_dst.numel() == n_dst,
+              "gcn_msg_sum_bwd: shape mismatch");
+  Tensor gx = at::empty_like(x), gw = zero_grad_w ? at::zeros_like(w) : at::empty_like(w);
+  if (gx.numel() == 0) return {gx, gw};
+  Entered en(x);
+  check_status(dglb_gcn_msg_sum_bwd(n_src, n_dst, nnz, x.size(1), i32(indptr_csr, "indptr"), i32(indices_csr, "indices"),
+                                    i32_opt(eids_csr, "eids"), x.data_ptr<float>(), w.data_ptr<float>(),
+                                    c_src.data_ptr<float>(), c_dst.data_ptr<float>(), grad_out.data_ptr<float>(),
+                                    gx.data_ptr<float>(), gw.data_ptr<float>(), en.stream), "dglb_gcn_msg_sum_bwd");
+  return {gx, gw};
+}
+
+int32_t* i32_mut(const OptTensor& t, const char* name, int64_t min_numel) {
+  if (!t.has_value()) return nullptr;
+  i32(*t, name);
+  TORCH_CHECK(t->numel() >= min_numel, name, " holds ", t->numel(), " entries, need ", min_numel);
+  return t->data_ptr<int32_t>();
+}
+
+// Fills the caller's fixed-size batch buffers IN PLACE (two launches, no allocation, no sync): capturable in a CUDA graph.
+// store  = [node_ptr, edge_ptr, u_src, u_dst, csc_indptr, csc_indices, csc_eids?, csr_indptr, csr_indices, csr_eids?]
+// batch  = [out_node_ptr, out_edge_ptr, status, src, dst, csc_indptr, csc_indices, csc_eids, csr_indptr, csr_indices,
+//           csr_eids, node_graph, node_map, edge_map]   (entries from `src` on may be None)
+void batch_build(const Tensor& graph_ids, const c10::List<OptTensor>& store_l, const c10::List<OptTensor>& batch_l,
+                 int64_t n_nodes_pad, int64_t n_edges_pad) {
+  std::vector<OptTensor> store, batch;
+  for (size_t i = 0; i < store_l.size(); ++i) store.push_back(store_l.get(i));
+  for (size_t i = 0; i < batch_l.size(); ++i) batch.push_back(batch_l.get(i));
+  TORCH_CHECK(store.size() == 10 && batch.size() == 14, "batch_build: expect 10 store tensors and 14 batch tensors");
+  const int64_t n_sel = graph_ids.numel();
+  dglb_batch_io_t io{};
+  io.n_sel = (int32_t)n_sel; io.n_nodes_pad = (int32_t)n_nodes_pad; io.n_edges_pad = (int32_t)n_edges_pad;
+  io.graph_ids = i32(graph_ids, "graph_ids");
+  TORCH_CHECK(store[0].has_value() && store[1].has_value() && batch[0].has_value() && batch[1].has_value(),
+              "batch_build: node_ptr / edge_ptr / out_node_ptr / out_edge_ptr are required");
+  io.node_ptr = i32(*store[0], "node_ptr"); io.edge_ptr = i32(*store[1], "edge_ptr");
+  io.u_src = i32_opt(store[2], "u_src"); io.u_dst = i32_opt(store[3], "u_dst");
+  io.u_csc_indptr = i32_opt(store[4], "u_csc_indptr"); io.u_csc_indices = i32_opt(store[5], "u_csc_indices");
+  io.u_csc_eids = i32_opt(store[6], "u_csc_eids");
+  io.u_csr_indptr = i32_opt(store[7], "u_csr_indptr"); io.u_csr_indices = i32_opt(store[8], "u_csr_indices");
+  io.u_csr_eids = i32_opt(store[9], "u_csr_eids");
+  int32_t* out_node_ptr = i32_mut(batch[0], "out_node_ptr", n_sel + 2);
+  int32_t* out_edge_ptr = i32_mut(batch[1], "out_edge_ptr", n_sel + 2);
+  int32_t* status = i32_mut(batch[2], "status", 1);
+  io.out_node_ptr = out_node_ptr; io.out_edge_ptr = out_edge_ptr;
+  io.src = i32_mut(batch[3], "src", n_edges_pad); io.dst = i32_mut(batch[4], "dst", n_edges_pad);
+  io.csc_indptr = i32_mut(batch[5], "csc_indptr", n_nodes_pad + 1);
+  io.csc_indices = i32_mut(batch[6], "csc_indices", n_edges_pad); io.csc_eids = i32_mut(batch[7], "csc_eids", n_edges_pad);
+  io.csr_indptr = i32_mut(batch[8], "csr_indptr", n_nodes_pad + 1);
+  io.csr_indices = i32_mut(batch[9], "csr_indices", n_edges_pad); io.csr_eids = i32_mut(batch[10], "csr_eids", n_edges_pad);
+  io.node_graph = i32_mut(batch[11], "node_graph", n_nodes_pad);
+  io.node_map = i32_mut(batch[12], "node_map", n_nodes_pad);
+  io.edge_map = i32_mut(batch[13], "edge_map", n_edges_pad);
+  Entered en(graph_ids);
+  check_status(dglb_batch_offsets(n_sel, io.graph_ids, io.node_ptr, io.edge_ptr, out_node_ptr, out_edge_ptr, n_nodes_pad,
+                                  n_edges_pad, status, en.stream), "dglb_batch_offsets");
+  check_status(dglb_batch_gather(&io, en.stream), "dglb_batch_gather");
+}
+
 int64_t abi_version() { return dglb_abi_version(); }
 int64_t default_hub_threshold(int64_t which, int64_t arg) {
   return which == 0 ? dglb_default_hub_threshold(arg) : (which == 1 ? dglb_default_row_hub_threshold(arg)
@@ -391,6 +477,12 @@ TORCH_LIBRARY(dglb200, m) {
   m.def("gat_bwd_dst(Tensor indptr, Tensor indices, Tensor? eids, Tensor ft, Tensor el, Tensor er, Tensor row_max, "
         "Tensor row_sum, Tensor grad_rst, float slope, float dropout_p, int seed, bool hub_segments, Tensor? hub_rows, "
         "Tensor? hub_seg_ptr, Tensor? hub_seg_hub, int[] hub_meta) -> (Tensor, Tensor)", &gat_bwd_dst);
+  m.def("gcn_msg_sum_fwd(Tensor indptr, Tensor indices, Tensor? eids, Tensor x, Tensor w, Tensor c_src, Tensor c_dst) -> Tensor",
+        &gcn_msg_sum_fwd);
+  m.def("gcn_msg_sum_bwd(Tensor indptr_csr, Tensor indices_csr, Tensor? eids_csr, Tensor x, Tensor w, Tensor c_src, "
+        "Tensor c_dst, Tensor grad_out, bool zero_grad_w) -> (Tensor, Tensor)", &gcn_msg_sum_bwd);
+  m.def("batch_build(Tensor graph_ids, Tensor?[] store, Tensor?[] batch, int n_nodes_pad, int n_edges_pad) -> ()",
+        &batch_build);
   m.def("gat_bwd_src(Tensor indptr, Tensor indices, Tensor? eids, int n_dst, Tensor ft, Tensor el, Tensor row_pack, "
         "Tensor grad_rst, float slope, float dropout_p, int seed, bool hub_segments, Tensor? hub_rows, Tensor? hub_seg_ptr, "
         "Tensor? hub_seg_hub, int[] hub_meta) -> (Tensor, Tensor)", &gat_bwd_src);

@@ -13,6 +13,7 @@ from . import utils  # noqa: F401
 from .transform import add_self_loop, remove_self_loop, to_bidirected, add_reverse_edges, reverse  # noqa: F401
 from .convert import from_networkx, from_scipy, to_networkx  # noqa: F401
 from .batch import batch  # noqa: F401
+from .batch_store import GraphStore, StaticBatch  # noqa: F401
 try:
     from . import nn  # noqa: F401
     from . import data  # noqa: F401

@@ -49,6 +49,16 @@ class HubStruct(ctypes.Structure):
 
 _hub_t = ctypes.POINTER(HubStruct)
 
+
+class BatchIO(ctypes.Structure):
+    """dglb_batch_io_t of include/dglb200.h."""
+    _fields_ = ([("n_sel", ctypes.c_int32), ("n_nodes_pad", ctypes.c_int32), ("n_edges_pad", ctypes.c_int32)] +
+                [(k, ctypes.c_void_p) for k in (
+                    "graph_ids", "node_ptr", "edge_ptr", "out_node_ptr", "out_edge_ptr", "u_src", "u_dst",
+                    "u_csc_indptr", "u_csc_indices", "u_csc_eids", "u_csr_indptr", "u_csr_indices", "u_csr_eids",
+                    "src", "dst", "csc_indptr", "csc_indices", "csc_eids", "csr_indptr", "csr_indices", "csr_eids",
+                    "node_graph", "node_map", "edge_map")])
+
 _SIGNATURES = {
     "dglb_abi_version": (_int, []),
     "dglb_last_error": (ctypes.c_char_p, []),
@@ -82,6 +92,10 @@ _SIGNATURES = {
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _hub_t, _vp]),
     "dglb_gat_fused_bwd_src": (_int, [_int, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _u64, _vp, _vp, _vp,
                                       _vp, _vp, _vp, _vp, _vp, _vp, _hub_t, _vp]),
+    "dglb_gcn_msg_sum_fwd": (_int, [_i64, _i64, _i64, _i64] + [_vp] * 9),
+    "dglb_gcn_msg_sum_bwd": (_int, [_i64, _i64, _i64, _i64] + [_vp] * 11),
+    "dglb_batch_offsets": (_int, [_i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "dglb_batch_gather": (_int, [ctypes.POINTER(BatchIO), _vp]),
 }
 
 
@@ -103,7 +117,7 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.dglb_abi_version() != 2:
+        if l.dglb_abi_version() != 3:
             raise DGLError("libdglb200.so ABI version mismatch")
         _lib = l
     return _lib
@@ -123,7 +137,7 @@ def ops():
                     "(there is no CPU / PyTorch fallback for the sparse kernels)" % path)
         torch.ops.load_library(TORCH_LIB_PATH)
         o = torch.ops.dglb200
-        if o.abi_version() != 2:
+        if o.abi_version() != 3:
             raise DGLError("libdglb200.so ABI version mismatch")
         _ops = o
     return _ops

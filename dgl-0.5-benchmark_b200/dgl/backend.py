@@ -214,3 +214,28 @@ def edge_softmax(gidx, logits, eids=None, norm_by="dst"):
 
 def gat_fused(gidx, ft, el, er, negative_slope=0.2, dropout_p=0.0, seed=0):
     return GATFused.apply(gidx, ft, el, er, float(negative_slope), float(dropout_p), int(seed))
+
+
+class GCNMsgSum(torch.autograd.Function):
+    """Fused message + reduce of the graph-classification GCN layer (main_dgl_molhiv_gcn.py:46,50-52):
+    sum over in-edges of (c[u] c[v]) relu(x[u] + w[e]).  The (E, D) message tensor is never materialised; the backward
+    recomputes the ReLU mask from x and w.  The norm vectors get no gradient (they are functions of the degrees)."""
+
+    @staticmethod
+    def forward(ctx, gidx, x, w, c_src, c_dst):
+        out = K._gcn_msg_sum_fwd(gidx, x, w, c_src, c_dst)
+        ctx.gidx = gidx
+        ctx.save_for_backward(x, w, c_src, c_dst)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, w, c_src, c_dst = ctx.saved_tensors
+        gx, gw = K._gcn_msg_sum_bwd(ctx.gidx, x, w, c_src, c_dst, grad_out)
+        return None, gx if ctx.needs_input_grad[1] else None, gw if ctx.needs_input_grad[2] else None, None, None
+
+
+def gcn_msg_sum(gidx, x, w, c_src, c_dst):
+    if c_src.requires_grad or c_dst.requires_grad:
+        raise DGLError("gcn_norm_relu_sum: the normalisation vectors are not differentiable inputs")
+    return GCNMsgSum.apply(gidx, x, w, c_src, c_dst)

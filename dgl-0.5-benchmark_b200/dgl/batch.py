@@ -23,6 +23,7 @@ def batch(graphs, ndata=None, edata=None):
         bg.ndata[k] = torch.cat([g.ndata[k] for g in graphs], 0)
     for k in graphs[0].edata.keys():
         bg.edata[k] = torch.cat([g.edata[k] for g in graphs], 0)
+    bg._batch_max_nodes = int(n_nodes.max())
     bg._batch_num_nodes = n_nodes.to(device)
     bg._batch_num_edges = n_edges.to(device)
     return bg

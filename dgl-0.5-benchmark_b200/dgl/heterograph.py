@@ -67,6 +67,8 @@ class DGLHeteroGraph:
         self._edge_frame = edge_frame if edge_frame is not None else Frame(gidx.n_edges)
         self._batch_num_nodes = None
         self._batch_num_edges = None
+        self._batch_max_nodes = None   # largest member graph, known on the host (readout: no hub-detection sync)
+        self._readout_index = None     # nodes -> member-graph relation used by the readout layers (dgl/nn/pytorch/glob.py)
 
     # ------------------------------------------------------------------ structure queries
     @property
@@ -150,6 +152,9 @@ class DGLHeteroGraph:
         s, d, e = frames if frames is not None else (self._src_frame, self._dst_frame, self._edge_frame)
         g = DGLHeteroGraph(gidx, s, d if self._is_block else None, e, is_block=self._is_block)
         g._batch_num_nodes, g._batch_num_edges = self._batch_num_nodes, self._batch_num_edges
+        g._batch_max_nodes = self._batch_max_nodes
+        if gidx is self._graph:
+            g._readout_index = self._readout_index
         return g
 
     def int(self):

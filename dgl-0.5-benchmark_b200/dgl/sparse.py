@@ -419,3 +419,29 @@ def _gat_bwd(gidx, ft, el, er, row_max, row_sum, grad_rst, slope, dropout_p, see
     row_pack, grad_er = _gat_bwd_dst(gidx, ft, el, er, row_max, row_sum, grad_rst, slope, dropout_p, seed)
     grad_ft, grad_el = _gat_bwd_src(gidx.csr(), ft, el, row_pack, grad_rst, slope, dropout_p, seed)
     return grad_ft, grad_el, grad_er
+
+
+# ------------------------------------------------------------------ batched small graphs (csrc/small_graph.cu)
+def _gcn_msg_sum_fwd(gidx, x, w, c_src, c_dst):
+    """out[v] = sum_{e=(u->v)} (c_src[u] c_dst[v]) relu(x[u] + w[e]) over the CSC, one launch."""
+    _check_float32(x, w, c_src, c_dst)
+    _capi.require_cuda(x, w, c_src, c_dst, gidx.src)
+    if w.shape[0] != gidx.n_edges or x.shape[0] != gidx.n_src:
+        raise DGLError("gcn_norm_relu_sum: expect x with %d rows and w with %d rows, got %d and %d"
+                       % (gidx.n_src, gidx.n_edges, x.shape[0], w.shape[0]))
+    csc = gidx.csc()
+    out = _capi.call(_capi.ops().gcn_msg_sum_fwd, csc.indptr, csc.indices, csc.eids, x.contiguous(), w.contiguous(),
+                     c_src.contiguous().view(-1), c_dst.contiguous().view(-1))
+    _capi.count_launch(1)
+    return out
+
+
+def _gcn_msg_sum_bwd(gidx, x, w, c_src, c_dst, grad_out):
+    """(grad_x, grad_w) over the CSR, one launch; grad_w is zero-filled first when the graph has edge slots outside
+    every CSR row (fixed-size padded batches: indptr[-1] < number of edge slots)."""
+    csr = gidx.csr()
+    padded = bool(gidx._c.get("padded_edge_slots", False))
+    gx, gw = _capi.call(_capi.ops().gcn_msg_sum_bwd, csr.indptr, csr.indices, csr.eids, x.contiguous(), w.contiguous(),
+                        c_src.contiguous().view(-1), c_dst.contiguous().view(-1), grad_out.contiguous(), padded)
+    _capi.count_launch(1)
+    return gx, gw

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define DGLB_ABI_VERSION 2
+#define DGLB_ABI_VERSION 3
 
 /* status codes */
 #define DGLB_OK 0
@@ -313,6 +313,75 @@ int dglb_gat_fused_bwd_src(int dtype, int64_t n_src, int64_t n_dst, int64_t nnz,
                            void* grad_ft /* (n_src,H,F) */, void* grad_el /* (n_src,H) */,
                            const dglb_hub_t* hub,
                            void* stream);
+
+/* ---------------------------------------------------------------- batched small graphs (BASELINE config 5)
+ * Fused GCN message + sum of the graph-classification scripts (main_dgl_molhiv_gcn.py:46,50-52 -- upstream runs the
+ * Python UDF `message` with torch ops on (E, D) tensors, then update_all(copy_e, sum)):
+ *   fwd (CSC over dst): out[v,:]    = sum_{e=(u->v), CSC order} (c_src[u] * c_dst[v]) * relu(x[u,:] + w[eid(e),:])
+ *   bwd (CSR over src): grad_w[e,:] = (x[u,:] + w[e,:] > 0) ? grad_out[v,:] * (c_src[u] * c_dst[v]) : 0     (every edge once)
+ *                       grad_x[u,:] = sum_{e=(u->v), CSR order} grad_w[e,:]
+ * x (n_src, D), w (nnz, D) in edge-id order, c_src (n_src), c_dst (n_dst), fp32.  Products and sums are rounded one by one
+ * (no FMA contraction), so the forward equals the unfused composite bit for bit.  grad_w rows of edges that appear in no
+ * CSR row (padding slots of a fixed-size batch) are not written: the caller zero-fills grad_w when such slots exist.
+ * Rows are walked sequentially by one thread per 4 columns: meant for the short rows of batched small graphs.
+ */
+int dglb_gcn_msg_sum_fwd(int64_t n_dst, int64_t n_src, int64_t nnz, int64_t feat_len,
+                         const int32_t* indptr, const int32_t* indices, const int32_t* eids,
+                         const float* x, const float* w, const float* c_src, const float* c_dst,
+                         float* out, void* stream);
+int dglb_gcn_msg_sum_bwd(int64_t n_src, int64_t n_dst, int64_t nnz, int64_t feat_len,
+                         const int32_t* indptr_csr, const int32_t* indices_csr, const int32_t* eids_csr,
+                         const float* x, const float* w, const float* c_src, const float* c_dst,
+                         const float* grad_out, float* grad_x, float* grad_w, void* stream);
+
+/* Device-side dgl.batch (replaces upstream python/dgl/batch.py::batch and the per-batch COO -> CSC / CSR conversions of
+ * the training loop, main_dgl_molhiv_gcn.py:101,163).  The dataset is ONE union graph on the device (member graph g owns
+ * nodes [node_ptr[g], node_ptr[g+1]) and edges [edge_ptr[g], edge_ptr[g+1]); its CSC / CSR come from dglb_coo_to_csr).
+ * Node ranges of member graphs are disjoint and increasing, so the stable CSC / CSR of a batch is the concatenation of
+ * the members' slices with shifted ids: bit-identical to dglb_coo_to_csr on the batched COO, without a sort.
+ *   dglb_batch_offsets: out_node_ptr / out_edge_ptr [n_sel + 2] = exclusive prefix sums of the selected graphs' node /
+ *     edge counts, then the totals, then the padded sizes (so rows [0, n_sel] of out_node_ptr are the CSC indptr of the
+ *     "node -> member graph" relation, the last row being the padding graph); status[0] (may be NULL) = 1 when the
+ *     batch exceeds the padded sizes.  One CTA.
+ *   dglb_batch_gather: fills the fixed-size buffers of dglb_batch_io_t (any output may be NULL).  Nodes / edge slots
+ *     beyond the batch's real counts are padding: isolated nodes of the padding member graph; edge slots that no
+ *     indptr range covers (their COO entries point at node n_nodes_pad - 1).
+ * Both are asynchronous and allocation-free: a whole training step including batch construction can be captured in one
+ * CUDA graph and replayed with only `graph_ids` changing.
+ */
+typedef struct dglb_batch_io_t {
+  int32_t n_sel, n_nodes_pad, n_edges_pad;
+  /* selection and the union graph (inputs) */
+  const int32_t* graph_ids;      /* [n_sel]      member graphs of the batch, in batch order            */
+  const int32_t* node_ptr;       /* [G + 1]                                                            */
+  const int32_t* edge_ptr;       /* [G + 1]                                                            */
+  const int32_t* out_node_ptr;   /* [n_sel + 2]  from dglb_batch_offsets                               */
+  const int32_t* out_edge_ptr;   /* [n_sel + 2]                                                        */
+  const int32_t* u_src;          /* [E_union]    COO of the union graph, edge-id order                 */
+  const int32_t* u_dst;
+  const int32_t* u_csc_indptr;   /* [N_union+1]  CSC (by dst) of the union graph                       */
+  const int32_t* u_csc_indices;
+  const int32_t* u_csc_eids;     /* NULL = identity                                                    */
+  const int32_t* u_csr_indptr;   /* CSR (by src)                                                       */
+  const int32_t* u_csr_indices;
+  const int32_t* u_csr_eids;
+  /* the batch (outputs, fixed size) */
+  int32_t* src;                  /* [n_edges_pad]                                                      */
+  int32_t* dst;
+  int32_t* csc_indptr;           /* [n_nodes_pad + 1]                                                  */
+  int32_t* csc_indices;          /* [n_edges_pad]                                                      */
+  int32_t* csc_eids;
+  int32_t* csr_indptr;
+  int32_t* csr_indices;
+  int32_t* csr_eids;
+  int32_t* node_graph;           /* [n_nodes_pad] member-graph slot of every node (padding: n_sel)     */
+  int32_t* node_map;             /* [n_nodes_pad] union-graph node of every batch node (feature gather) */
+  int32_t* edge_map;             /* [n_edges_pad] union-graph edge id of every batch edge              */
+} dglb_batch_io_t;
+int dglb_batch_offsets(int64_t n_sel, const int32_t* graph_ids, const int32_t* node_ptr, const int32_t* edge_ptr,
+                       int32_t* out_node_ptr, int32_t* out_edge_ptr,
+                       int64_t n_nodes_pad, int64_t n_edges_pad, int32_t* status, void* stream);
+int dglb_batch_gather(const dglb_batch_io_t* io, void* stream);
 
 #ifdef __cplusplus
 }

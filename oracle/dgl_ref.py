@@ -338,3 +338,39 @@ def gat_forward(g, ft, attn_l, attn_r, negative_slope=0.2):
     a = edge_softmax(g, e)
     rst, _ = _gspmm(g, "mul", "sum", ft, a)
     return rst, a, el, er
+
+
+# ----------------------------------------------------------------------------- batched small graphs
+def gcn_message_sum(g, x, w, c_src, c_dst):
+    """The message UDF + reducer of the graph-classification GCN layer, written out as in the reference:
+    end_to_end/full_graph/graph_classification/main_dgl_molhiv_gcn.py:50-52 (norm = c[src] * c[dst];
+    m = norm * relu(x[src] + w)) followed by update_all(..., fn.sum('m', 'h')) (:46) = gspmm(copy_rhs, sum) in CSC order.
+    Elementwise float32 with one rounding per operation, like the torch ops the UDF runs."""
+    x, w = _f32(x), _f32(w)
+    c_src, c_dst = _f32(c_src).reshape(-1), _f32(c_dst).reshape(-1)
+    norm = (c_src[g.src] * c_dst[g.dst]).astype(np.float32)[:, None]
+    m = (norm * np.maximum(x[g.src] + w, np.float32(0))).astype(np.float32)
+    return _gspmm(g, "copy_rhs", "sum", None, m)[0]
+
+
+def gcn_message_sum_backward(g, x, w, c_src, c_dst, grad_out):
+    """Gradients of gcn_message_sum w.r.t. x and w in float64 (the reference gets them from torch autograd through
+    the same ops: d m = grad_out[dst]; d relu = d m * norm where x[src] + w > 0; d x = scatter-add over src)."""
+    x64, w64 = np.asarray(x, np.float64), np.asarray(w, np.float64)
+    norm = (np.asarray(c_src, np.float64).reshape(-1)[g.src] * np.asarray(c_dst, np.float64).reshape(-1)[g.dst])[:, None]
+    pre = _f32(x)[g.src] + _f32(w)                      # the mask is decided in float32, like the forward
+    gw = np.where(pre > 0, np.asarray(grad_out, np.float64)[g.dst] * norm, 0.0)
+    gx = np.zeros_like(x64)
+    np.add.at(gx, g.src, gw)
+    return gx, gw
+
+
+def batch_graphs(members):
+    """dgl.batch restated (upstream python/dgl/batch.py::batch; call site main_dgl_molhiv_gcn.py:163 through
+    GraphDataLoader): members = [(src, dst, n_nodes), ...]; node ids of member i are shifted by the node counts of the
+    members before it, edges keep member order.  Returns (OracleGraph, node_offsets, edge_offsets)."""
+    n_off = np.concatenate([[0], np.cumsum([m[2] for m in members])]).astype(np.int64)
+    e_off = np.concatenate([[0], np.cumsum([len(m[0]) for m in members])]).astype(np.int64)
+    src = np.concatenate([np.asarray(m[0], np.int64) + o for m, o in zip(members, n_off)]) if members else np.zeros(0)
+    dst = np.concatenate([np.asarray(m[1], np.int64) + o for m, o in zip(members, n_off)]) if members else np.zeros(0)
+    return OracleGraph(src, dst, int(n_off[-1]), int(n_off[-1])), n_off, e_off

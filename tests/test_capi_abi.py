@@ -40,7 +40,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     lib = ctypes.CDLL(built_lib)
     for name in _header_functions():
         assert hasattr(lib, name), "libdglb200.so does not export %s" % name
-    assert lib.dglb_abi_version() == 2
+    assert lib.dglb_abi_version() == 3
 
 
 def test_ctypes_signatures_match_header_arity(built_lib):
@@ -95,10 +95,10 @@ def test_torch_extension_loads_and_fails_loudly_on_cpu_tensors():
     import torch
     from dgl import _capi
     o = _capi.ops()
-    assert o.abi_version() == 2
+    assert o.abi_version() == 3
     for name in ("coo_to_csr", "csr_degrees", "is_identity_perm", "find_hub_rows", "edge_stage_plan", "edge_stage",
                  "gspmm", "gsddmm_csr", "gsddmm_coo", "edge_softmax_fwd", "edge_softmax_bwd", "gat_fwd", "gat_bwd_dst",
-                 "gat_bwd_src", "default_hub_threshold"):
+                 "gat_bwd_src", "default_hub_threshold", "gcn_msg_sum_fwd", "gcn_msg_sum_bwd", "batch_build"):
         assert hasattr(o, name), name
     assert o.default_hub_threshold(0, 602) == 256 and o.default_hub_threshold(1, 64) == 128
     with pytest.raises(_capi.DGLError, match="CUDA-only"):
@@ -106,3 +106,21 @@ def test_torch_extension_loads_and_fails_loudly_on_cpu_tensors():
     ip = torch.tensor([0, 1, 2], dtype=torch.int32)
     with pytest.raises(_capi.DGLError, match="CUDA-only"):
         _capi.call(o.gspmm, ip, ip[:2], None, 2, 4, 0, torch.ones(2, 4), None, [4], [4], [4], None, None, 0, *_capi.NO_HUB)
+
+
+def test_small_graph_entry_points_validate_arguments_without_a_gpu(built_lib):
+    """dglb_batch_gather / dglb_gcn_msg_sum_* reject inconsistent argument sets before any CUDA call."""
+    from dgl import _capi
+    l = _capi.lib()
+    assert l.dglb_batch_gather(None, None) == -1 and b"io is null" in l.dglb_last_error()
+    io = _capi.BatchIO()
+    io.n_sel, io.n_nodes_pad, io.n_edges_pad = 2, 8, 8
+    for k in ("graph_ids", "node_ptr", "edge_ptr", "out_node_ptr", "out_edge_ptr", "csc_indptr"):
+        setattr(io, k, 8)
+    assert l.dglb_batch_gather(ctypes.byref(io), None) == -1 and b"union CSC" in l.dglb_last_error()
+    assert l.dglb_gcn_msg_sum_fwd(4, 4, 3, 8, ctypes.c_void_p(8), None, None, None, None, None, ctypes.c_void_p(8),
+                                  ctypes.c_void_p(8), None) == -1
+    assert b"null operand" in l.dglb_last_error()
+    with pytest.raises(_capi.DGLError, match="CUDA-only"):
+        import torch
+        _capi.call(_capi.ops().batch_build, torch.zeros(2, dtype=torch.int32), [None] * 10, [None] * 14, 4, 4)

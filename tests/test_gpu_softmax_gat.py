@@ -57,6 +57,44 @@ def test_edge_softmax_group_shapes(oracle, cuda, nn_, ne, H):
     assert_close_sumscaled(n(zt.grad), wantg, scale, rtol=2e-5, what="edge_softmax bwd")
 
 
+@pytest.mark.parametrize("nn_,ne", [(300, 4001), (257, 2103), (33, 9001), (5000, 1200), (700, 60002)])
+@pytest.mark.parametrize("H", [1, 2, 3, 4, 8, 12, 32])
+def test_edge_softmax_identity_order_window_kernel(oracle, cuda, nn_, ne, H):
+    """dst-sorted edge lists (CSC position == edge id) take the shared-memory window kernel: spans that start at any
+    float offset, tensors whose length is not a multiple of 4 floats (the last vector is fetched by hand), CTAs whose
+    rows need several fills, single rows longer than the window (33 nodes x 9001 edges x 32 heads), mostly-empty rows,
+    hub rows left to the segmented kernels (power-law graph)."""
+    kind = "powerlaw" if ne > 50000 else "uniform"
+    og, g, src, dst = graphs(oracle, nn_, nn_, ne, seed=ne + H, kind=kind, order="dst_sorted")
+    assert g._graph.csc().eids is None        # identity permutation dropped at build time -> window kernel
+    rng = np.random.default_rng(ne + H)
+    z = (2 * rng.standard_normal((ne, H))).astype(np.float32)
+    want = oracle.edge_softmax(og, z)
+    zt = t(z).requires_grad_(True)
+    got = dgl.ops.edge_softmax(g, zt)
+    np.testing.assert_allclose(n(got), want, rtol=1e-5, atol=1e-30)
+    gout = rng.standard_normal((ne, H)).astype(np.float32)
+    got.backward(t(gout))
+    wantg = oracle.edge_softmax_backward(og, want, gout)
+    acc = np.zeros((nn_, H))
+    np.add.at(acc, dst, np.abs(want * gout).astype(np.float64))
+    scale = np.abs(want) * (np.abs(gout) + acc[dst])
+    assert_close_sumscaled(n(zt.grad), wantg, scale, rtol=2e-5, what="edge_softmax bwd (window kernel)")
+
+
+def test_edge_softmax_window_kernel_matches_row_kernel(oracle, cuda, monkeypatch):
+    """The window kernel and the register-resident row kernel reduce a row in the same association
+    (strided per-lane partials, xor tree) when their group widths agree; here only closeness is required."""
+    og, g, src, dst = graphs(oracle, 2000, 2000, 100000, seed=9, order="dst_sorted")
+    z = t((2 * np.random.default_rng(9).standard_normal((100000, 4))).astype(np.float32))
+    a = dgl.ops.edge_softmax(g, z)
+    want = oracle.edge_softmax(og, n(z))
+    np.testing.assert_allclose(n(a), want, rtol=1e-5, atol=1e-30)
+    sums = torch.zeros(2000, 4, device="cuda").index_add_(0, t(dst).long(), a)
+    deg = np.bincount(dst, minlength=2000)
+    np.testing.assert_allclose(n(sums)[deg > 0], 1.0, rtol=1e-5)
+
+
 def test_edge_softmax_norm_by_src(oracle, cuda):
     og, g, src, dst = graphs(oracle, 100, 100, 1500, seed=4)
     z = np.random.default_rng(4).standard_normal((1500, 2)).astype(np.float32)

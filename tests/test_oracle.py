@@ -180,3 +180,39 @@ def test_broadcast_offsets_match_numpy(oracle):
     assert not bc["use_bcast"] and bc["out_len"] == 4 and bc["reduce_size"] == 8
     with pytest.raises(ValueError):
         oracle.calc_bcast("add", (3, 2), (4, 2))
+
+
+def test_gcn_message_sum_vs_torch_autograd_fp64(oracle):
+    """main_dgl_molhiv_gcn.py:50-52 + :46 restated (oracle.gcn_message_sum) against the same math through torch autograd
+    in float64: forward within float32 rounding, backward formulas exact."""
+    import torch
+    rng = np.random.default_rng(5)
+    n, e, D = 60, 400, 9
+    src, dst = rng.integers(0, n, e), rng.integers(0, n, e)
+    g = oracle.OracleGraph(src, dst, n, n)
+    x, w = rng.standard_normal((n, D)).astype(np.float32), rng.standard_normal((e, D)).astype(np.float32)
+    c = ((g.in_degrees() + 1) ** -0.5).astype(np.float32)
+    gout = rng.standard_normal((n, D)).astype(np.float32)
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    wt = torch.tensor(w, dtype=torch.float64, requires_grad=True)
+    ct = torch.tensor(c, dtype=torch.float64)
+    s, d = torch.from_numpy(src), torch.from_numpy(dst)
+    m = (ct[s] * ct[d])[:, None] * torch.relu(xt[s] + wt)
+    h = torch.zeros(n, D, dtype=torch.float64).index_add_(0, d, m)
+    h.backward(torch.tensor(gout, dtype=torch.float64))
+    np.testing.assert_allclose(oracle.gcn_message_sum(g, x, w, c, c), h.detach().numpy(), rtol=1e-5, atol=1e-6)
+    gx, gw = oracle.gcn_message_sum_backward(g, x, w, c, c, gout)
+    np.testing.assert_allclose(gx, xt.grad.numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(gw, wt.grad.numpy(), rtol=1e-12, atol=1e-12)
+
+
+def test_batch_graphs_shifts_ids_and_keeps_member_order(oracle):
+    a = (np.array([0, 1, 2]), np.array([1, 2, 0]), 3)
+    b = (np.array([], dtype=np.int64), np.array([], dtype=np.int64), 2)       # a member without edges
+    c = (np.array([1, 0]), np.array([0, 0]), 2)
+    g, n_off, e_off = oracle.batch_graphs([a, b, c])
+    assert n_off.tolist() == [0, 3, 5, 7] and e_off.tolist() == [0, 3, 3, 5]
+    assert g.src.tolist() == [0, 1, 2, 6, 5] and g.dst.tolist() == [1, 2, 0, 5, 5]
+    indptr, indices, data = g.csc
+    assert indptr.tolist() == [0, 1, 2, 3, 3, 3, 5, 5]
+    assert indices.tolist() == [2, 0, 1, 6, 5] and data.tolist() == [2, 0, 1, 3, 4]
