@@ -373,6 +373,27 @@ int dglb_gcn_msg_sum_bwd(int64_t n_src, int64_t n_dst, int64_t nnz, int64_t feat
                          static_cast<cudaStream_t>(stream));
 }
 
+int dglb_cat_embed_sum_fwd(int64_t n_rows, int64_t n_columns, int64_t feat_len, const int64_t* x, const int32_t* offsets_host,
+                           const float* table, float* out, void* stream) {
+  DGLB_CHECK_ARG(n_rows >= 0 && n_columns >= 0 && feat_len >= 0 && offsets_host, "cat_embed_sum_fwd: bad sizes / offsets");
+  DGLB_CHECK_ARG(n_rows == 0 || feat_len == 0 || (out && (n_columns == 0 || (x && table))), "cat_embed_sum_fwd: null array");
+  return cat_embed_sum(false, n_rows, n_columns, feat_len, x, offsets_host, table, nullptr, out, nullptr, 0,
+                       static_cast<cudaStream_t>(stream));
+}
+
+size_t dglb_cat_embed_sum_bwd_workspace_bytes(int64_t n_rows, int64_t n_table_rows, int64_t feat_len) {
+  return cat_embed_bwd_workspace_bytes(n_rows, n_table_rows, feat_len);
+}
+
+int dglb_cat_embed_sum_bwd(int64_t n_rows, int64_t n_columns, int64_t feat_len, const int64_t* x, const int32_t* offsets_host,
+                           const float* grad_out, float* grad_table, void* workspace, size_t workspace_bytes, void* stream) {
+  DGLB_CHECK_ARG(n_rows >= 0 && n_columns >= 0 && feat_len >= 0 && offsets_host, "cat_embed_sum_bwd: bad sizes / offsets");
+  DGLB_CHECK_ARG(n_columns == 0 || feat_len == 0 || offsets_host[n_columns] == 0 || (grad_table && (n_rows == 0 || (x && grad_out))),
+                 "cat_embed_sum_bwd: null array");
+  return cat_embed_sum(true, n_rows, n_columns, feat_len, x, offsets_host, nullptr, grad_out, grad_table, workspace,
+                       workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int dglb_batch_offsets(int64_t n_sel, const int32_t* graph_ids, const int32_t* node_ptr, const int32_t* edge_ptr,
                        int32_t* out_node_ptr, int32_t* out_edge_ptr, int64_t n_nodes_pad, int64_t n_edges_pad,
                        int32_t* status, void* stream) {
@@ -398,6 +419,12 @@ int dglb_batch_gather(const dglb_batch_io_t* io, void* stream) {
                      (io->csr_indices == nullptr) == (io->csr_eids == nullptr),
                  "batch_gather: indices and eids outputs come in pairs");
   return batch_gather(*io, static_cast<cudaStream_t>(stream));
+}
+
+int dglb_copy_rows_indexed(int64_t n_idx, const int32_t* idx, int64_t row_bytes, const void* src, void* dst, void* stream) {
+  DGLB_CHECK_ARG(n_idx >= 0 && row_bytes >= 0, "copy_rows_indexed: negative size");
+  DGLB_CHECK_ARG(n_idx == 0 || row_bytes == 0 || (idx && src && dst), "copy_rows_indexed: null array");
+  return copy_rows_indexed(n_idx, idx, row_bytes, src, dst, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -109,5 +109,11 @@ int batch_offsets(int64_t n_sel, const int32_t* graph_ids, const int32_t* node_p
                   int32_t* out_node_ptr, int32_t* out_edge_ptr, int64_t n_nodes_pad, int64_t n_edges_pad, int32_t* status,
                   cudaStream_t stream);
 int batch_gather(const dglb_batch_io_t& io, cudaStream_t stream);
+int cat_embed_sum(bool bwd, int64_t n_rows, int64_t K, int64_t D, const int64_t* x, const int32_t* offsets_host,
+                  const float* T, const float* g, float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t cat_embed_bwd_workspace_bytes(int64_t n_rows, int64_t n_table_rows, int64_t D);
+
+// row_copy.cu
+int copy_rows_indexed(int64_t n_idx, const int32_t* idx, int64_t row_bytes, const void* src, void* dst, cudaStream_t stream);
 
 }  // namespace dglb

@@ -12,6 +12,14 @@
 //     that produces grad_x (sum over a node's out-edges in CSR order, deterministic) and grad_w (one row per edge) in a
 //     single pass, recomputing the ReLU mask from x + w instead of saving the (E, D) message.
 //
+//  1b. Sum of categorical embeddings (ogb.graphproppred.mol_encoder AtomEncoder / BondEncoder, main_dgl_molhiv_gcn.py:28,72:
+//     out[i,:] = sum_k table_k[x[i,k],:], 9 atom / 3 bond columns).  torch runs one embedding lookup + one add per
+//     column forward and, backward, a radix sort + segmented reduction per column: 15 encoders x ~40 launches were
+//     half of a captured training iteration (profiles/r02_molhiv_graph_profile.txt).  Here the tables are one
+//     concatenated matrix: one forward kernel (same order of additions as the column loop: bit-identical) and one
+//     DETERMINISTIC backward kernel (a CTA per table row scans the rows of x in order; the tables have a few hundred
+//     rows in total, so that is O(N) work per CTA for a batch of small graphs).
+//
 //  2. Device-side dgl.batch (upstream python/dgl/batch.py::batch + the COO->CSC/CSR conversions it triggers,
 //     main_dgl_molhiv_gcn.py:101,163): the dataset lives on the device as ONE union graph (all member graphs side by
 //     side) with its CSC / CSR built once.  Because the node ranges of member graphs are disjoint and increasing, the CSC of
@@ -131,6 +139,188 @@ int gcn_msg_sum_bwd(int64_t n_src, int64_t D, const int32_t* indptr, const int32
     gcn_msg_sum_bwd_kernel<1><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(n_src, (int)D, ncol, indptr, indices, eids, x, w,
                                                                                  c_src, c_dst, gout, gx, gw);
   DGLB_LAUNCH_CHECK("gcn_msg_sum_bwd_kernel");
+  return DGLB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ categorical embeddings
+struct CatEmbedParams {
+  const int64_t* __restrict__ x;   // (n_rows, K) categorical codes (int64, as OGB stores them)
+  const float* __restrict__ T;     // (R, D) concatenated tables
+  const float* __restrict__ g;     // bwd: (n_rows, D)
+  float* __restrict__ out;         // fwd: (n_rows, D); bwd: (R, D)
+  int64_t n_rows;
+  int K, D, ncol, R;
+  int off[DGLB_MAX_CAT_COLUMNS + 1];   // first row of every column's table; off[K] = R
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kBlockThreads) cat_embed_sum_fwd_kernel(const CatEmbedParams p) {
+  const int64_t idx = (int64_t)blockIdx.x * kBlockThreads + threadIdx.x;
+  const int64_t row = idx / p.ncol;
+  if (row >= p.n_rows) return;
+  const int col = (int)(idx - row * p.ncol) * VEC;
+  float acc[VEC];
+  for (int k = 0; k < p.K; ++k) {
+    const int64_t r = (int64_t)p.off[k] + __ldg(p.x + row * p.K + k);
+    const FVec<VEC> t = ldg_vec<VEC>(p.T + r * p.D + col);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = k == 0 ? t.v[v] : __fadd_rn(acc[v], t.v[v]);
+  }
+  FVec<VEC> o;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) o.v[v] = p.K > 0 ? acc[v] : 0.f;
+  st_vec<VEC>(p.out + row * p.D + col, o);
+}
+
+// Grid (table row r, chunk s): the CTA sums grad_out over the rows of x in chunk s = [s * kCatChunk, (s+1) * kCatChunk)
+// whose code in column k(r) is r - off[k].  Inside the chunk warp w owns a contiguous eighth: it compacts the matching
+// rows into its shared-memory list (ballot + popcount, order preserved, coalesced scan), then sums them with several rows
+// in flight, each lane holding its columns in registers; the 8 per-warp sums are combined in warp order and written to
+// partial[s][r][:].  A second kernel adds the chunks in order: deterministic, no atomics.  (Two earlier versions -- a
+// per-row "load code, compare, branch" loop, then one CTA per table row -- took ~150 us per call: the tables have few
+// rows, binary columns match half of x, and a single CTA was summing ~1 800 rows.)
+constexpr int kCatChunk = 512;
+constexpr int kCatWarps = kBlockThreads / 32;
+constexpr int kCatMaxCols = 8;   // float4 columns per lane: D <= 32 * 4 * 8 = 1024
+
+template <bool V4>
+__global__ void __launch_bounds__(kBlockThreads) cat_embed_sum_bwd_kernel(const CatEmbedParams p, float* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char cat_smem[];
+  constexpr int kPer = kCatChunk / kCatWarps;
+  int* lists = reinterpret_cast<int*>(cat_smem);                                  // [kCatWarps][kPer]
+  float* sums = reinterpret_cast<float*>(cat_smem + sizeof(int) * kCatChunk);      // [kCatWarps][D]
+  const int r = blockIdx.x;
+  int k = 0;
+  while (k + 1 < p.K && p.off[k + 1] <= r) ++k;
+  const int64_t code = r - p.off[k];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int* my = lists + warp * kPer;
+  const int D = p.D;
+  const int nvec = (D + 127) / 128;           // float4 columns per lane (V4: D % 4 == 0, 16-byte aligned rows)
+  float acc[kCatMaxCols][4];
+#pragma unroll
+  for (int c = 0; c < kCatMaxCols; ++c)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[c][v] = 0.f;
+
+  const int64_t lo = (int64_t)blockIdx.y * kCatChunk + (int64_t)warp * kPer;
+  const int64_t hi = min(p.n_rows, lo + kPer);
+  int n = 0;
+  for (int64_t i0 = lo; i0 < hi; i0 += 32) {
+    const int64_t i = i0 + lane;
+    const bool m = i < hi && __ldg(p.x + i * p.K + k) == code;
+    const unsigned b = __ballot_sync(FULL_MASK, m);
+    if (m) my[n + __popc(b & ((1u << lane) - 1u))] = (int)(i - lo);
+    n += __popc(b);
+  }
+  __syncwarp();
+  if constexpr (V4) {
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {          // rows in order; the loads of up to 4 rows are issued before their adds
+      const float* g = p.g + (lo + my[j]) * D;
+#pragma unroll
+      for (int c = 0; c < kCatMaxCols; ++c) {
+        const int col = (c * 32 + lane) * 4;
+        if (c < nvec && col < D) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(g + col));
+          acc[c][0] = __fadd_rn(acc[c][0], t.x); acc[c][1] = __fadd_rn(acc[c][1], t.y);
+          acc[c][2] = __fadd_rn(acc[c][2], t.z); acc[c][3] = __fadd_rn(acc[c][3], t.w);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kCatMaxCols; ++c) {
+      const int col = (c * 32 + lane) * 4;
+      if (c < nvec && col < D) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) sums[warp * D + col + v] = acc[c][v];
+      }
+    }
+  } else {
+    for (int j = 0; j < n; ++j) {
+      const float* g = p.g + (lo + my[j]) * D;
+#pragma unroll
+      for (int c = 0; c < kCatMaxCols * 4; ++c) {
+        const int col = c * 32 + lane;
+        if (col < D) acc[c >> 2][c & 3] = __fadd_rn(acc[c >> 2][c & 3], __ldg(g + col));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < kCatMaxCols * 4; ++c) {
+      const int col = c * 32 + lane;
+      if (col < D) sums[warp * D + col] = acc[c >> 2][c & 3];
+    }
+  }
+  __syncthreads();
+  float* dst = partial + ((int64_t)blockIdx.y * p.R + r) * D;
+  for (int col = threadIdx.x; col < D; col += kBlockThreads) {
+    float a = sums[col];
+    for (int w = 1; w < kCatWarps; ++w) a = __fadd_rn(a, sums[w * D + col]);
+    dst[col] = a;
+  }
+}
+
+// out[r,:] = partial[0][r,:] + partial[1][r,:] + ... (chunk order)
+__global__ void __launch_bounds__(kBlockThreads)
+cat_embed_combine_kernel(const float* __restrict__ partial, float* __restrict__ out, int64_t rd, int n_chunks) {
+  const int64_t i = (int64_t)blockIdx.x * kBlockThreads + threadIdx.x;
+  if (i >= rd) return;
+  float a = partial[i];
+  for (int s = 1; s < n_chunks; ++s) a = __fadd_rn(a, partial[(int64_t)s * rd + i]);
+  out[i] = a;
+}
+
+size_t cat_embed_bwd_workspace_bytes(int64_t n_rows, int64_t n_table_rows, int64_t D) {
+  const int64_t chunks = (n_rows + kCatChunk - 1) / kCatChunk;
+  return chunks > 1 ? (size_t)chunks * (size_t)n_table_rows * (size_t)D * sizeof(float) : 0;
+}
+
+int cat_embed_sum(bool bwd, int64_t n_rows, int64_t K, int64_t D, const int64_t* x, const int32_t* offsets_host,
+                  const float* T, const float* g, float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  if (K > DGLB_MAX_CAT_COLUMNS) {
+    set_error("cat_embed_sum: at most %d categorical columns (got %lld)", DGLB_MAX_CAT_COLUMNS, (long long)K);
+    return DGLB_E_UNSUPPORTED;
+  }
+  CatEmbedParams p;
+  p.x = x; p.T = T; p.g = g; p.out = out; p.n_rows = n_rows; p.K = (int)K; p.D = (int)D;
+  for (int k = 0; k <= K; ++k) p.off[k] = offsets_host[k];
+  p.R = offsets_host[K];
+  const bool v4 = D % 4 == 0 && aligned16(T) && aligned16(out) && (!bwd || aligned16(g));
+  p.ncol = (int)(v4 ? D / 4 : D);
+  if (!bwd) {
+    if (n_rows == 0 || D == 0) return DGLB_OK;
+    const int64_t blocks = (n_rows * p.ncol + kBlockThreads - 1) / kBlockThreads;
+    if (v4) cat_embed_sum_fwd_kernel<4><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+    else cat_embed_sum_fwd_kernel<1><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+    DGLB_LAUNCH_CHECK("cat_embed_sum_fwd_kernel");
+  } else {
+    if (p.R == 0 || D == 0) return DGLB_OK;
+    if (D > 32 * 4 * kCatMaxCols) {
+      set_error("cat_embed_sum_bwd: feature width %lld exceeds %d", (long long)D, 32 * 4 * kCatMaxCols);
+      return DGLB_E_UNSUPPORTED;
+    }
+    const int64_t chunks = n_rows > 0 ? (n_rows + kCatChunk - 1) / kCatChunk : 1;
+    const size_t need = cat_embed_bwd_workspace_bytes(n_rows, p.R, D);
+    if (need > 0 && (!workspace || workspace_bytes < need)) {
+      set_error("cat_embed_sum_bwd: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+      return DGLB_E_WORKSPACE;
+    }
+    if (chunks > 65535) {
+      set_error("cat_embed_sum_bwd: %lld rows exceed the supported batch size", (long long)n_rows);
+      return DGLB_E_UNSUPPORTED;
+    }
+    float* partial = chunks > 1 ? static_cast<float*>(workspace) : out;   // a single chunk writes the result directly
+    const size_t smem = sizeof(int) * kCatChunk + (size_t)kCatWarps * (size_t)D * sizeof(float);
+    const dim3 grid((unsigned)p.R, (unsigned)chunks);
+    if (v4) cat_embed_sum_bwd_kernel<true><<<grid, kBlockThreads, smem, stream>>>(p, partial);
+    else cat_embed_sum_bwd_kernel<false><<<grid, kBlockThreads, smem, stream>>>(p, partial);
+    if (chunks > 1) {
+      const int64_t rd = (int64_t)p.R * D;
+      cat_embed_combine_kernel<<<(unsigned)((rd + kBlockThreads - 1) / kBlockThreads), kBlockThreads, 0, stream>>>(
+          partial, out, rd, (int)chunks);
+    }
+    DGLB_LAUNCH_CHECK("cat_embed_sum_bwd_kernel");
+  }
   return DGLB_OK;
 }
 

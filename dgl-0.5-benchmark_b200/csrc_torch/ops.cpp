@@ -395,6 +395,37 @@ std::tuple<Tensor, Tensor> gcn_msg_sum_bwd(const Tensor& indptr_csr, const Tenso
   return {gx, gw};
 }
 
+// x (n, K) int64 codes; table (R, D); offsets: K + 1 table starts (host ints)
+Tensor cat_embed_sum_fwd(const Tensor& x, const Tensor& table, at::IntArrayRef offsets) {
+  need_cuda(x, "x"); need_cuda(table, "table");
+  TORCH_CHECK(x.scalar_type() == at::kLong && x.dim() == 2 && table.scalar_type() == at::kFloat && table.dim() == 2,
+              "cat_embed_sum: expect int64 codes (n, K) and a float32 table (R, D)");
+  TORCH_CHECK((int64_t)offsets.size() == x.size(1) + 1 && offsets.back() == table.size(0), "cat_embed_sum: offsets must list K + 1 table starts ending at R");
+  std::vector<int32_t> off(offsets.begin(), offsets.end());
+  Tensor out = at::empty({x.size(0), table.size(1)}, table.options());
+  if (out.numel() == 0) return out;
+  Entered en(table);
+  check_status(dglb_cat_embed_sum_fwd(x.size(0), x.size(1), table.size(1), x.data_ptr<int64_t>(), off.data(),
+                                      table.data_ptr<float>(), out.data_ptr<float>(), en.stream), "dglb_cat_embed_sum_fwd");
+  return out;
+}
+
+Tensor cat_embed_sum_bwd(const Tensor& x, const Tensor& grad_out, at::IntArrayRef offsets) {
+  need_cuda(x, "x"); need_cuda(grad_out, "grad_out");
+  TORCH_CHECK(x.scalar_type() == at::kLong && x.dim() == 2 && grad_out.scalar_type() == at::kFloat && grad_out.dim() == 2 &&
+                  grad_out.size(0) == x.size(0) && (int64_t)offsets.size() == x.size(1) + 1, "cat_embed_sum_bwd: shape mismatch");
+  std::vector<int32_t> off(offsets.begin(), offsets.end());
+  Tensor gt = at::empty({offsets.back(), grad_out.size(1)}, grad_out.options());
+  if (gt.numel() == 0) return gt;
+  const size_t ws_bytes = dglb_cat_embed_sum_bwd_workspace_bytes(x.size(0), offsets.back(), grad_out.size(1));
+  Tensor ws = at::empty({(int64_t)std::max<size_t>(ws_bytes, 4)}, grad_out.options().dtype(at::kByte));
+  Entered en(grad_out);
+  check_status(dglb_cat_embed_sum_bwd(x.size(0), x.size(1), grad_out.size(1), x.data_ptr<int64_t>(), off.data(),
+                                      grad_out.data_ptr<float>(), gt.data_ptr<float>(), ws.data_ptr(), ws_bytes, en.stream),
+               "dglb_cat_embed_sum_bwd");
+  return gt;
+}
+
 int32_t* i32_mut(const OptTensor& t, const char* name, int64_t min_numel) {
   if (!t.has_value()) return nullptr;
   i32(*t, name);
@@ -442,6 +473,23 @@ void batch_build(const Tensor& graph_ids, const c10::List<OptTensor>& store_l, c
   check_status(dglb_batch_gather(&io, en.stream), "dglb_batch_gather");
 }
 
+// ------------------------------------------------------------------ halo exchange
+// dst[idx] = src[idx] row-wise, in place (src may be a peer GPU's symmetric-memory view); runs on the CURRENT stream of
+// dst's device
+void copy_rows_indexed(const Tensor& src, Tensor dst, const Tensor& idx) {
+  need_cuda(src, "src"); need_cuda(dst, "dst");
+  TORCH_CHECK(src.scalar_type() == dst.scalar_type() && src.dim() >= 1 && dst.dim() == src.dim(),
+              "copy_rows_indexed: src and dst must have the same dtype and rank");
+  const int64_t n = idx.numel();
+  if (n == 0) return;
+  const int64_t row_bytes = (dst.numel() / std::max<int64_t>(dst.size(0), 1)) * dst.element_size();
+  TORCH_CHECK(src.size(0) > 0 && (src.numel() / src.size(0)) * src.element_size() == row_bytes,
+              "copy_rows_indexed: row sizes differ");
+  Entered en(dst);
+  check_status(dglb_copy_rows_indexed(n, i32(idx, "idx"), row_bytes, src.data_ptr(), dst.data_ptr(), en.stream),
+               "dglb_copy_rows_indexed");
+}
+
 int64_t abi_version() { return dglb_abi_version(); }
 int64_t default_hub_threshold(int64_t which, int64_t arg) {
   return which == 0 ? dglb_default_hub_threshold(arg) : (which == 1 ? dglb_default_row_hub_threshold(arg)
@@ -481,8 +529,11 @@ TORCH_LIBRARY(dglb200, m) {
         &gcn_msg_sum_fwd);
   m.def("gcn_msg_sum_bwd(Tensor indptr_csr, Tensor indices_csr, Tensor? eids_csr, Tensor x, Tensor w, Tensor c_src, "
         "Tensor c_dst, Tensor grad_out, bool zero_grad_w) -> (Tensor, Tensor)", &gcn_msg_sum_bwd);
+  m.def("cat_embed_sum_fwd(Tensor x, Tensor table, int[] offsets) -> Tensor", &cat_embed_sum_fwd);
+  m.def("cat_embed_sum_bwd(Tensor x, Tensor grad_out, int[] offsets) -> Tensor", &cat_embed_sum_bwd);
   m.def("batch_build(Tensor graph_ids, Tensor?[] store, Tensor?[] batch, int n_nodes_pad, int n_edges_pad) -> ()",
         &batch_build);
+  m.def("copy_rows_indexed(Tensor src, Tensor(a!) dst, Tensor idx) -> ()", &copy_rows_indexed);
   m.def("gat_bwd_src(Tensor indptr, Tensor indices, Tensor? eids, int n_dst, Tensor ft, Tensor el, Tensor row_pack, "
         "Tensor grad_rst, float slope, float dropout_p, int seed, bool hub_segments, Tensor? hub_rows, Tensor? hub_seg_ptr, "
         "Tensor? hub_seg_hub, int[] hub_meta) -> (Tensor, Tensor)", &gat_bwd_src);

@@ -94,8 +94,12 @@ _SIGNATURES = {
                                       _vp, _vp, _vp, _vp, _vp, _vp, _hub_t, _vp]),
     "dglb_gcn_msg_sum_fwd": (_int, [_i64, _i64, _i64, _i64] + [_vp] * 9),
     "dglb_gcn_msg_sum_bwd": (_int, [_i64, _i64, _i64, _i64] + [_vp] * 11),
+    "dglb_cat_embed_sum_fwd": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "dglb_cat_embed_sum_bwd_workspace_bytes": (ctypes.c_size_t, [_i64, _i64, _i64]),
+    "dglb_cat_embed_sum_bwd": (_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, ctypes.c_size_t, _vp]),
     "dglb_batch_offsets": (_int, [_i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "dglb_batch_gather": (_int, [ctypes.POINTER(BatchIO), _vp]),
+    "dglb_copy_rows_indexed": (_int, [_i64, _vp, _i64, _vp, _vp, _vp]),
 }
 
 

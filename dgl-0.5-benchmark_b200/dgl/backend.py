@@ -239,3 +239,26 @@ def gcn_msg_sum(gidx, x, w, c_src, c_dst):
     if c_src.requires_grad or c_dst.requires_grad:
         raise DGLError("gcn_norm_relu_sum: the normalisation vectors are not differentiable inputs")
     return GCNMsgSum.apply(gidx, x, w, c_src, c_dst)
+
+
+class CatEmbedSum(torch.autograd.Function):
+    """out[i] = sum_k table[off[k] + x[i,k]] (AtomEncoder / BondEncoder of the OGB molecule scripts) as one kernel each
+    way; the backward is deterministic (no atomics, no sort)."""
+
+    @staticmethod
+    def forward(ctx, x, table, offsets):
+        _capi = K._capi
+        _capi.require_cuda(x, table)
+        out = _capi.call(_capi.ops().cat_embed_sum_fwd, x.contiguous(), table.contiguous(), offsets)
+        _capi.count_launch(1)
+        ctx.offsets = offsets
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        _capi = K._capi
+        x, = ctx.saved_tensors
+        gt = _capi.call(_capi.ops().cat_embed_sum_bwd, x.contiguous(), grad_out.contiguous(), ctx.offsets)
+        _capi.count_launch(1)
+        return None, gt, None

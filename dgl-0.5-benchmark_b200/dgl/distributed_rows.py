@@ -43,6 +43,16 @@ three peers | the last four); block g is aggregated as soon as its last shard ha
 kernels), accumulating into the output, while the later shards are still in flight.  The local block needs no
 communication at all.  Block order changes the summation order (tolerance, not bit-identity); exact=True waits for
 every shard and runs the single-kernel path instead.
+
+Halo exchange (north_star: "halo and full feature all-gather").  At build time every rank lists, per peer, the sorted
+unique rows of that peer which its CSC slice (forward) / CSR slice (backward) actually references.  When a list covers
+less than HALO_MAX_FRACTION of the peer's rows, the pull of that shard becomes an indexed row copy
+(csrc/row_copy.cu: dst[idx] = src[idx], an SM kernel on the copy stream reading the peer's symmetric buffer over NVLink)
+instead of a whole-shard copy-engine transfer: only referenced rows cross the link.  Rows land at the same positions
+of the gather buffer, so the blocks, their column ids and the summation order are untouched and results stay
+bit-identical to the full exchange; unreferenced rows of the buffer are never written and never read.  On the uniform
+random graphs of the benchmark (average degree 25-50 over 8 ranks) every rank references nearly every row and the
+exchange stays a full one; graphs with locality (banded / clustered orderings) move a fraction of the bytes.
 """
 import numpy as np
 import torch
@@ -51,6 +61,7 @@ import torch.distributed as dist
 from .heterograph import create_block
 from . import ops
 from . import sparse as K_
+from . import _capi
 
 
 def balanced_row_ranges(in_degrees, world):
@@ -92,6 +103,8 @@ class RowPartition:
         self._copy_streams = None
         self.peer_group_sizes = None
         self.exact = True            # peer-to-peer autograd path: single-kernel (bit-identical) or blocked aggregation
+        self.halo = {"fwd": None, "bwd": None}   # per direction: [int32 device row list per peer, or None = whole shard]
+        self.halo_rows = {"fwd": None, "bwd": None}   # per direction: rows referenced per peer (host ints, diagnostics)
 
     # ------------------------------------------------------------------ construction
     def pad_ids(self, ids):
@@ -102,6 +115,25 @@ class RowPartition:
         local = ids - los[own]
         k = local // self.chunk_rows
         return (k * self.world + own) * self.chunk_rows + (local - k * self.chunk_rows), k
+
+    HALO_MAX_FRACTION = 0.5   # pull a peer's shard row by row when fewer than this share of its rows is referenced
+
+    def _halo_lists(self, cols_global, device):
+        """Per peer: sorted unique LOCAL row ids (within the peer's range) among `cols_global`, as an int32 device
+        tensor when they are few enough for the indexed pull, else None (whole shard); plus the referenced-row counts."""
+        his = np.array([r[1] for r in self.ranges])
+        los = np.array([r[0] for r in self.ranges])
+        uniq = np.unique(cols_global)
+        own = np.searchsorted(his, uniq, side="right")
+        lists, counts = [], []
+        for p in range(self.world):
+            rows = (uniq[own == p] - los[p]).astype(np.int32)
+            counts.append(int(rows.shape[0]))
+            if p != self.rank and rows.shape[0] < self.HALO_MAX_FRACTION * self.sizes[p]:
+                lists.append(torch.from_numpy(rows).to(device))
+            else:
+                lists.append(None)
+        return lists, counts
 
     @staticmethod
     def default_peer_groups(world):
@@ -153,6 +185,9 @@ class RowPartition:
         # destination nodes (whose dZ rows are gathered) and the "destinations" the local source nodes
         part.bwd_graph = create_block((torch.from_numpy(part.pad_ids(dst[selb])[0]), torch.from_numpy(src[selb] - lo)),
                                       part.n_pad, hi - lo).int().to(device)
+        if chunks == 1:
+            part.halo["fwd"], part.halo_rows["fwd"] = part._halo_lists(src[sel], device)
+            part.halo["bwd"], part.halo_rows["bwd"] = part._halo_lists(dst[selb], device)
         if peer_groups is not None:
             assert chunks == 1, "peer blocks use the one-slot-per-rank gather layout"
             part.peer_group_sizes = list(peer_groups)
@@ -196,6 +231,7 @@ class RowPartition:
         # ONE copy stream: measured at 8 GPUs (profiles/r02_p2p_copy_bench_n8.jsonl) a single in-order stream of pulls
         # moves 70 MB shards at 609 GB/s per rank, two streams 562, four 371
         self._copy_streams = [torch.cuda.Stream()]
+        self.halo_bytes_pulled = self.full_bytes_pulled = 0   # bytes requested over NVLink by this rank (host counters)
         return self
 
     @property
@@ -215,12 +251,13 @@ class RowPartition:
             self._p2p[key] = (t, hdl, views)
         return self._p2p[key]
 
-    def p2p_gather(self, xs, order="operand"):
+    def p2p_gather(self, xs, order="operand", bwd=False, halo=True):
         """Start the exchange of a list of local row tensors (order: "operand" = all shards of xs[0], then xs[1], ...;
         "group" = peer group by peer group across the operands).  Returns [(buffer, events)] per operand: the padded
         gather buffer (the local shard is in place in stream order) and events[k], k = 1..P-1, which fire once the
         shard of rank (rank + k) mod P has landed.  Two device-side barriers per call (not per operand): peers have
-        finished reading what the symmetric buffers held before / every rank has published its new rows."""
+        finished reading what the symmetric buffers held before / every rank has published its new rows.
+        bwd: the operands feed the backward block (rows referenced by the CSR slice); halo=False forces whole shards."""
         P, cr, main = self.world, self.chunk_rows, torch.cuda.current_stream()
         seen, slots, gbufs = {}, [], []
         for x in xs:
@@ -245,6 +282,7 @@ class RowPartition:
             groups.append([k for k in range(lo, min(lo + gsz, P)) if k > 0])   # ring step 0 is the local shard
             lo += gsz
         all_events = [[None] * P for _ in xs]
+        halo_lists = self.halo["bwd" if bwd else "fwd"] if halo else None
         for st in self._copy_streams:
             st.wait_event(ready)
         i = 0
@@ -258,9 +296,15 @@ class RowPartition:
             n_peer = self.sizes[peer]
             st = self._copy_streams[i % len(self._copy_streams)]
             i += 1
+            idx = halo_lists[peer] if halo_lists is not None else None
             with torch.cuda.stream(st):
-                if n_peer:
+                if n_peer and idx is not None:
+                    if idx.numel():      # halo: only the rows this rank's slice references, fetched by an SM kernel
+                        _capi.call(_capi.ops().copy_rows_indexed, views[peer], gbuf[peer * cr: peer * cr + n_peer], idx)
+                        self.halo_bytes_pulled += idx.numel() * gbuf[0].numel() * gbuf.element_size()
+                elif n_peer:
                     gbuf[peer * cr: peer * cr + n_peer].copy_(views[peer][:n_peer], non_blocking=True)
+                    self.full_bytes_pulled += n_peer * gbuf[0].numel() * gbuf.element_size()
                 ev = torch.cuda.Event()
                 ev.record(st)
             all_events[oi][k] = ev
@@ -455,7 +499,7 @@ class _PartitionedCopyUSum(torch.autograd.Function):
                 deg = part.local_graph.in_degrees().clamp(min=1).to(dz_local.dtype)
                 dz_local = dz_local / deg.view(-1, 1)
             if part.p2p:
-                (buf, ev), = part.p2p_gather([dz_local])
+                (buf, ev), = part.p2p_gather([dz_local], bwd=True)
                 return None, part.blocked_copy_u_sum(buf, ev, exact=part.exact, bwd=True), None
             dz_full = part.all_gather_rows(dz_local)
             dx = ops.gspmm(part.bwd_graph, "copy_lhs", "sum", dz_full, None)
@@ -486,11 +530,11 @@ class _PartitionedGAT(torch.autograd.Function):
         with torch.no_grad():
             grad_rst = grad_rst.contiguous()
             if part.p2p:   # grad_rst is known now: it travels while the destination pass runs
-                (grad_full, ev_g), = part.p2p_gather([grad_rst])
+                (grad_full, ev_g), = part.p2p_gather([grad_rst], bwd=True)
             row_pack, grad_er = K_._gat_bwd_dst(part.local_graph._graph, ft_full, el_full, er.contiguous(), row_max,
                                                 row_sum, grad_rst, slope, dropout_p, seed, eids=part.global_eids("fwd"))
             if part.p2p:
-                (pack_full, ev_p), = part.p2p_gather([row_pack])
+                (pack_full, ev_p), = part.p2p_gather([row_pack], bwd=True)
                 part._wait(ev_g, part.world - 1)
                 part._wait(ev_p, part.world - 1)
             else:

@@ -4,4 +4,4 @@ from .spmm import *  # noqa: F401,F403
 from .sddmm import *  # noqa: F401,F403
 from .edge_softmax import *  # noqa: F401,F403
 from .gat import gat_attention  # noqa: F401
-from .gcn import gcn_norm_relu_sum  # noqa: F401
+from .gcn import gcn_norm_relu_sum, categorical_embedding_sum  # noqa: F401

@@ -72,6 +72,8 @@ def captured_runner(model, store, batches, bs, lr=1e-3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=60)
+    ap.add_argument("--batch-sizes", default="64,128,256")
+    ap.add_argument("--profile", default="", help="write a torch.profiler kernel table of the captured iteration (first batch size) here")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     ds = DglGraphPropPredDataset("ogbg-molhiv", num_graphs=4096)
@@ -81,7 +83,7 @@ def main():
     opt_fused = torch.optim.Adam(fused_model.parameters(), lr=1e-3)
     all_samples = [ds[i] for i in range(256 * 8)]
     store = dgl.GraphStore([s[0] for s in all_samples], torch.stack([s[1] for s in all_samples]), device=dev)
-    for bs in (64, 128, 256):
+    for bs in [int(b) for b in args.batch_sizes.split(",")]:
         samples = all_samples[:bs * 8]
         host_batches = [(dgl.batch([s[0] for s in samples[j * bs:(j + 1) * bs]]),
                          torch.stack([s[1] for s in samples[j * bs:(j + 1) * bs]])) for j in range(8)]
@@ -147,6 +149,22 @@ def main():
         torch.cuda.synchronize()
         graph_ms = (time.perf_counter() - t0) / args.iters * 1e3
         graph_dev_ms = ev0.elapsed_time(ev1) / args.iters
+        if args.profile:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for i in range(5):
+                    run(pinned[i % 8])
+                torch.cuda.synchronize()
+            evs = [e for e in prof.key_averages() if e.device_time_total > 0]
+            evs.sort(key=lambda e: -e.device_time_total)
+            tot = sum(e.device_time_total for e in evs)
+            with open(args.profile, "w") as f:
+                f.write("# molhiv GCN, batch %d, one CUDA-graph replay: device time %.3f ms over %d kernels / memcpys (torch.profiler, 5 replays)\n"
+                        % (bs, tot / 5e3, sum(e.count for e in evs) // 5))
+                f.write("# share  ms/iter  calls/iter  kernel\n")
+                for e in evs[:60]:
+                    f.write("%5.1f%%  %8.4f  %5d  %s\n" % (100 * e.device_time_total / tot, e.device_time_total / 5e3, e.count // 5, e.key[:150]))
+            args.profile = ""
         g0 = dev_batches[0][0]
         iters_per_epoch = -(-32901 // bs)
         iters_per_epoch = -(-32901 // bs)

@@ -334,6 +334,23 @@ int dglb_gcn_msg_sum_bwd(int64_t n_src, int64_t n_dst, int64_t nnz, int64_t feat
                          const float* x, const float* w, const float* c_src, const float* c_dst,
                          const float* grad_out, float* grad_x, float* grad_w, void* stream);
 
+/* Sum of categorical embeddings (ogb.graphproppred.mol_encoder AtomEncoder / BondEncoder as used by
+ * main_dgl_molhiv_gcn.py:28,72): x (n_rows, n_columns) int64 codes, `table` (offsets_host[n_columns], feat_len) the
+ * columns' embedding tables stacked, offsets_host[k] (HOST array, n_columns + 1 entries) the first row of column k's table.
+ *   fwd: out[i,:]        = table[off[0] + x[i,0],:] + table[off[1] + x[i,1],:] + ...      (in column order: bit-identical to
+ *                          the sequential `out = out + emb_k(x[:, k])` loop of the encoder)
+ *   bwd: grad_table[r,:] = sum over rows i with off[k] + x[i,k] == r of grad_out[i,:]   (deterministic: rows are summed in
+ *                          order inside 512-row chunks, chunks in order; no atomics, no sort.  workspace >=
+ *                          dglb_cat_embed_sum_bwd_workspace_bytes(n_rows, offsets_host[n_columns], feat_len); feat_len <= 1024)
+ */
+#define DGLB_MAX_CAT_COLUMNS 16
+int dglb_cat_embed_sum_fwd(int64_t n_rows, int64_t n_columns, int64_t feat_len, const int64_t* x,
+                           const int32_t* offsets_host, const float* table, float* out, void* stream);
+size_t dglb_cat_embed_sum_bwd_workspace_bytes(int64_t n_rows, int64_t n_table_rows, int64_t feat_len);
+int dglb_cat_embed_sum_bwd(int64_t n_rows, int64_t n_columns, int64_t feat_len, const int64_t* x,
+                           const int32_t* offsets_host, const float* grad_out, float* grad_table,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* Device-side dgl.batch (replaces upstream python/dgl/batch.py::batch and the per-batch COO -> CSC / CSR conversions of
  * the training loop, main_dgl_molhiv_gcn.py:101,163).  The dataset is ONE union graph on the device (member graph g owns
  * nodes [node_ptr[g], node_ptr[g+1]) and edges [edge_ptr[g], edge_ptr[g+1]); its CSC / CSR come from dglb_coo_to_csr).
@@ -382,6 +399,15 @@ int dglb_batch_offsets(int64_t n_sel, const int32_t* graph_ids, const int32_t* n
                        int32_t* out_node_ptr, int32_t* out_edge_ptr,
                        int64_t n_nodes_pad, int64_t n_edges_pad, int32_t* status, void* stream);
 int dglb_batch_gather(const dglb_batch_io_t* io, void* stream);
+
+/* ---------------------------------------------------------------- halo exchange of the 1-D row partition
+ * (new: the reference is single-GPU; BASELINE.json north_star asks for "halo and full feature all-gather".)
+ *   dst[idx[i], :] = src[idx[i], :]   for i in [0, n_idx), rows of row_bytes bytes (a multiple of 4)
+ * src is typically a peer GPU's buffer mapped over NVLink (symmetric memory), dst the local gather buffer's slot for that
+ * peer, idx the sorted unique rows of the peer that the rank's CSC / CSR slice references.  Rows keep their position, so
+ * nothing downstream changes and results stay bit-identical to a full exchange.
+ */
+int dglb_copy_rows_indexed(int64_t n_idx, const int32_t* idx, int64_t row_bytes, const void* src, void* dst, void* stream);
 
 #ifdef __cplusplus
 }

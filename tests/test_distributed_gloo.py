@@ -212,6 +212,94 @@ def test_peer_group_blocks_match_single_process(oracle, world):
         np.testing.assert_allclose(np.sort(np.concatenate(r[6]).ravel()), np.sort(want_dot[sel].ravel()), rtol=1e-6)
 
 
+def _banded_edges(n, e, width, seed):
+    """edges u -> v with |u - v| <= width (mod-free): a graph with locality, where a rank references only the rows of
+    its neighbours next to the range boundary -- the case the halo exchange is for."""
+    rng = np.random.default_rng(seed)
+    dst = rng.integers(0, n, size=e)
+    src = np.clip(dst + rng.integers(-width, width + 1, size=e), 0, n - 1)
+    return src.astype(np.int64), dst.astype(np.int64)
+
+
+def _halo_worker(rank, world, port, q):
+    import sys
+    for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle_backend
+    from dgl.distributed_rows import RowPartition
+    n, e, D = 600, 9000, 6
+    src, dst = _banded_edges(n, e, 20, seed=5)
+    X = np.random.default_rng(3).random((n, D), dtype=np.float32)
+    with oracle_backend.installed():
+        part = RowPartition.build(src, dst, n, world, rank, torch.device("cpu"),
+                                  peer_groups=RowPartition.default_peer_groups(world))
+        xl = torch.from_numpy(X[part.lo:part.hi])
+        full = part.all_gather_rows(xl)
+        cr = part.chunk_rows
+        res = {}
+        for direction, bwd in (("fwd", False), ("bwd", True)):
+            # what the halo pull leaves in the gather buffer: the local shard, the listed rows of each peer, NaN elsewhere
+            buf = torch.full_like(full, float("nan"))
+            buf[rank * cr: rank * cr + part.n_local_rows] = full[rank * cr: rank * cr + part.n_local_rows]
+            pulled = 0
+            for p_ in range(world):
+                if p_ == rank:
+                    continue
+                idx = part.halo[direction][p_]
+                if idx is None:                       # whole shard
+                    buf[p_ * cr: p_ * cr + part.sizes[p_]] = full[p_ * cr: p_ * cr + part.sizes[p_]]
+                    pulled += part.sizes[p_]
+                else:
+                    buf[p_ * cr + idx.long()] = full[p_ * cr + idx.long()]
+                    pulled += int(idx.numel())
+            out = part.blocked_copy_u_sum(buf, [None] * world, exact=True, bwd=bwd)
+            res[direction] = (out.numpy(), pulled, [None if l is None else l.numpy() for l in part.halo[direction]],
+                              part.halo_rows[direction])
+    q.put((rank, part.lo, part.hi, res, list(part.sizes)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_halo_lists_cover_exactly_the_referenced_rows(oracle, world):
+    """Halo exchange: per peer, the row list equals the unique rows of that peer the rank's CSC (forward) / CSR (backward)
+    slice references; a gather buffer holding ONLY the local shard and those rows (NaN everywhere else) aggregates to the
+    single-process result bit for bit; on a banded graph the lists are a small fraction of a full exchange."""
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_halo_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n, e, D = 600, 9000, 6
+    src, dst = _banded_edges(n, e, 20, seed=5)
+    X = np.random.default_rng(3).random((n, D), dtype=np.float32)
+    og = oracle.OracleGraph(src, dst, n, n)
+    want = {"fwd": oracle.gspmm(og, "copy_lhs", "sum", X, None), "bwd": oracle.gspmm(og.reverse(), "copy_lhs", "sum", X, None)}
+    ranges = [(r[1], r[2]) for r in res]
+    for direction in ("fwd", "bwd"):
+        got = np.concatenate([r[3][direction][0] for r in res])
+        assert np.array_equal(got, want[direction])              # no NaN leaked in: every referenced row was pulled
+        for rank, lo, hi, out, sizes in res:
+            _, pulled, lists, counts = out[direction]
+            mine = (dst >= lo) & (dst < hi) if direction == "fwd" else (src >= lo) & (src < hi)
+            cols = (src if direction == "fwd" else dst)[mine]
+            for p_, (plo, phi) in enumerate(ranges):
+                ref = np.unique(cols[(cols >= plo) & (cols < phi)]) - plo
+                assert counts[p_] == len(ref)
+                if p_ != rank and lists[p_] is not None:
+                    assert np.array_equal(lists[p_], ref)
+                    assert len(ref) < 0.5 * sizes[p_]
+            assert pulled < 0.25 * (n - (hi - lo))               # banded graph: a fraction of the full exchange
+
+
 def test_balanced_row_ranges():
     from dgl.distributed_rows import balanced_row_ranges
     deg = np.array([10, 0, 0, 10, 1, 1, 1, 1, 6, 10])

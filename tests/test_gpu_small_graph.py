@@ -149,7 +149,7 @@ def test_padded_captured_training_step_matches_eager_unpadded(oracle, cuda):
     torch.manual_seed(0)
     ref = M.GCN(dim=64, layers=3, dropout=0.0, fused=False).to(cuda)
     fast = M.GCN(dim=64, layers=3, dropout=0.0, fused=True).to(cuda)
-    fast.load_state_dict(ref.state_dict())
+    M.copy_parameters(ref, fast)
     opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-3)
     opt_fast = torch.optim.Adam(fast.parameters(), lr=1e-3, capturable=True)
     lossf = torch.nn.functional.binary_cross_entropy_with_logits
@@ -212,6 +212,43 @@ def test_padded_captured_training_step_matches_eager_unpadded(oracle, cuda):
         graph.replay()
         got.append(float(static_loss))
     np.testing.assert_allclose(got, want, rtol=2e-4)
-    for (k, a), (_, b) in zip(ref.state_dict().items(), fast.state_dict().items()):
-        if a.dtype.is_floating_point:
-            np.testing.assert_allclose(n(b), n(a), rtol=0, atol=5e-4, err_msg=k)
+    fsd = fast.state_dict()
+    for k, a in ref.state_dict().items():
+        if a.dtype.is_floating_point and k in fsd:
+            np.testing.assert_allclose(n(fsd[k]), n(a), rtol=0, atol=5e-4, err_msg=k)
+    np.testing.assert_allclose(n(fast.atom.weight), n(torch.cat([e.weight for e in ref.atom.embs], 0)), rtol=0, atol=5e-4)
+
+
+@pytest.mark.parametrize("n_rows,D", [(1, 256), (777, 256), (5000, 64), (300, 7), (0, 32)])
+def test_categorical_embedding_sum(cuda, n_rows, D):
+    """AtomEncoder arithmetic (sum of 9 per-column embedding lookups, in column order) in one kernel: forward bit-exact
+    against the sequential torch loop, backward against torch's embedding backward in float64 (deterministic here)."""
+    dims = [119, 4, 12, 12, 10, 6, 6, 2, 2]
+    rng = np.random.default_rng(n_rows + D)
+    x = torch.from_numpy(np.stack([rng.integers(0, d, size=n_rows) for d in dims], 1).astype(np.int64)).to(cuda)
+    table = torch.randn(sum(dims), D, device=cuda, requires_grad=True)
+    got = dgl.ops.categorical_embedding_sum(x, table, dims)
+    offs = np.concatenate([[0], np.cumsum(dims)])
+    want = 0
+    for k in range(len(dims)):
+        want = want + table.detach()[offs[k] + x[:, k]]
+    if n_rows:
+        assert torch.equal(got, want)
+    gout = torch.randn(n_rows, D, device=cuda)
+    got.backward(gout)
+    t64 = table.detach().double().requires_grad_(True)
+    w64 = 0
+    for k in range(len(dims)):
+        w64 = w64 + t64[offs[k] + x[:, k]]
+    if n_rows:
+        w64.backward(gout.double())
+        scale = torch.zeros_like(t64)
+        for k in range(len(dims)):
+            scale.index_add_(0, offs[k] + x[:, k], gout.double().abs())
+        assert_close_sumscaled(n(table.grad), n(t64.grad), n(scale), rtol=1e-5, what="categorical_embedding_sum grad")
+        g2 = table.grad.clone()
+        table.grad = None
+        dgl.ops.categorical_embedding_sum(x, table, dims).backward(gout)
+        assert torch.equal(table.grad, g2)                       # deterministic
+    else:
+        assert table.grad is None or float(table.grad.abs().sum()) == 0.0
