@@ -24,6 +24,7 @@ struct SddmmParams {
   const float* __restrict__ U;  // lhs rows gathered by source id
   const float* __restrict__ V;  // rhs rows, one per destination row
   float* __restrict__ out;
+  const int32_t* __restrict__ row_order;  // [n_rows] rows by non-increasing nnz (null: natural order)
   const int32_t* __restrict__ hub_rows;
   const int32_t* __restrict__ seg_ptr;  // [n_hub+1] first segment of each hub row
   const int32_t* __restrict__ seg_hub;  // [n_seg]   hub index of each segment
@@ -56,6 +57,7 @@ __device__ __forceinline__ void group_work(const SddmmParams& p, int64_t& row, i
     row = ((int64_t)blockIdx.x * kBlockThreads + threadIdx.x) >> p.log2G;
     j0 = 0; n = 0;
     if (row < p.n_rows) {
+      if (p.row_order) row = __ldg(p.row_order + row);   // degree-ordered hand-out (see dglb_hub_t)
       const int s = __ldg(p.indptr + row);
       const int d = __ldg(p.indptr + row + 1) - s;
       if (d <= p.hub_threshold) { j0 = s; n = d; }
@@ -423,6 +425,7 @@ int sddmm_csr_fast_f32(int op, int64_t n_dst, int64_t n_src, int64_t nnz, const 
   p.indptr = indptr; p.indices = indices; p.eids = eids; p.U = Uf; p.V = Vf; p.out = out;
   const bool use_hub = hub && hub->n_hub > 0 && hub->n_seg > 0 && hub->rows && hub->seg_ptr && hub->seg_hub &&
                        hub->seg_len > 0;
+  p.row_order = hub ? hub->row_order : nullptr;
   p.hub_rows = use_hub ? hub->rows : nullptr;
   p.seg_ptr = use_hub ? hub->seg_ptr : nullptr;
   p.seg_hub = use_hub ? hub->seg_hub : nullptr;

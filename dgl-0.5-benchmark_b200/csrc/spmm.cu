@@ -44,6 +44,7 @@ struct SpmmParams {
   int32_t* __restrict__ arg_u;
   int32_t* __restrict__ arg_e;
   const float* __restrict__ row_scale;
+  const int32_t* __restrict__ row_order; // [n_rows] rows by non-increasing nnz (null: natural order)
   const int32_t* __restrict__ hub_rows;
   const int32_t* __restrict__ seg_ptr;   // [n_hub+1]
   const int32_t* __restrict__ seg_hub;   // [n_seg]
@@ -214,10 +215,12 @@ __global__ void __launch_bounds__(kBlockThreads, spmm_min_ctas<OP, RED>(RMODE, C
 spmm_rows_kernel(const SpmmParams p) {
   const int G = p.G;
   const int lg = threadIdx.x & (G - 1);
-  const int64_t row = ((int64_t)blockIdx.x * kBlockThreads + threadIdx.x) >> p.log2G;
+  int64_t row = ((int64_t)blockIdx.x * kBlockThreads + threadIdx.x) >> p.log2G;
   int row_start = 0, deg = 0;
   bool active = row < p.n_rows;
   if (active) {
+    // degree-ordered hand-out: the groups of a warp get rows of (nearly) equal length, longest rows first
+    if (p.row_order) row = __ldg(p.row_order + row);
     row_start = __ldg(p.indptr + row);
     deg = __ldg(p.indptr + row + 1) - row_start;
     if (deg > p.hub_threshold) { active = false; deg = 0; }  // left to the hub kernel
@@ -626,6 +629,7 @@ int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz
     if (rr % 4 ? (reinterpret_cast<uintptr_t>(W) % 8 != 0) : (reinterpret_cast<uintptr_t>(W) % 16 != 0)) vec = 0;
     if (vec > 0 && xl / vec <= 32) {
       SpmmParams p;
+      p.row_order = nullptr;
       memset(&p, 0, sizeof(p));
       p.indptr = indptr; p.indices = indices; p.eids = eids; p.X = X; p.W = W; p.out = out; p.row_scale = row_scale;
       p.n_rows = n_rows; p.D = (int)b.out_len; p.xlen = (int)xl; p.rhs_len = (int)rr;
@@ -642,6 +646,7 @@ int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz
                         (op == DGLB_OP_MUL && reduce == DGLB_REDUCE_SUM));
   if (rmode >= 0 && fast_op && b.out_len < (1 << 30)) {
     SpmmParams p;
+    p.row_order = nullptr;
     p.indptr = indptr; p.indices = indices; p.eids = eids;
     p.X = X; p.W = W; p.out = out; p.arg_u = arg_u; p.arg_e = arg_e;
     p.row_scale = row_scale;
@@ -665,6 +670,7 @@ int spmm_csr_f32(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nnz
       p.ws_val = nullptr; p.ws_au = nullptr; p.ws_ae = nullptr;
     }
     p.n_rows = n_rows; p.D = (int)b.out_len; p.rhs_len = (int)b.rhs_len; p.inner = (int)inner;
+    p.row_order = hub ? hub->row_order : nullptr;
     p.hub_threshold = use_hub ? hub->threshold : INT32_MAX;
     p.accumulate = (flags & DGLB_SPMM_ACCUMULATE) ? 1 : 0;
     p.zero_inf = (flags & DGLB_SPMM_ZERO_INF) ? 1 : 0;
@@ -722,6 +728,7 @@ int spmm_csr_bf16(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nn
   if (n_rows == 0 || D == 0) return DGLB_OK;
   if (D >= (1 << 30)) return DGLB_E_UNSUPPORTED;
   SpmmParams p;
+  p.row_order = nullptr;
   p.indptr = indptr; p.indices = indices; p.eids = nullptr;
   p.X = static_cast<const float*>(X); p.W = nullptr; p.out = static_cast<float*>(out);
   p.arg_u = nullptr; p.arg_e = nullptr; p.row_scale = row_scale;
@@ -739,6 +746,7 @@ int spmm_csr_bf16(int op, int reduce, int64_t n_rows, int64_t n_cols, int64_t nn
     p.hub_rows = nullptr; p.seg_ptr = nullptr; p.seg_hub = nullptr; p.seg_len = 0; p.ws_val = nullptr;
   }
   p.ws_au = nullptr; p.ws_ae = nullptr;
+  p.row_order = hub ? hub->row_order : nullptr;
   p.hub_threshold = use_hub ? hub->threshold : INT32_MAX;
   p.skip_rows = 0;
   {

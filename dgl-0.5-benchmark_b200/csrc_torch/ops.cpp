@@ -69,8 +69,16 @@ struct Entered {
 
 // hub_meta = {n_hub, n_seg, seg_len, threshold}; returns false when no hub rows were passed
 bool make_hub(dglb_hub_t* h, const OptTensor& rows, const OptTensor& seg_ptr, const OptTensor& seg_hub,
-              const OptTensor& light, at::IntArrayRef meta) {
-  if (!rows.has_value() || meta.size() != 4 || meta[0] <= 0) return false;
+              const OptTensor& light, at::IntArrayRef meta, const OptTensor& order = std::nullopt) {
+  h->row_order = i32_opt(order, "hub row_order");
+  if (!rows.has_value() || meta.size() != 4 || meta[0] <= 0) {
+    if (!order.has_value()) return false;
+    // no hub rows, but a degree-ordered row hand-out for the row kernels
+    h->rows = h->seg_ptr = h->seg_hub = h->light_indptr = nullptr;
+    h->n_hub = h->n_seg = h->seg_len = 0; h->threshold = INT32_MAX;
+    h->workspace = nullptr; h->workspace_bytes = 0;
+    return true;
+  }
   h->rows = i32(*rows, "hub rows");
   h->seg_ptr = i32_opt(seg_ptr, "hub seg_ptr");
   h->seg_hub = i32_opt(seg_hub, "hub seg_hub");
@@ -166,7 +174,8 @@ std::tuple<Tensor, Tensor, Tensor> gspmm(
     const Tensor& indptr, const Tensor& indices, const OptTensor& eids, int64_t n_cols, int64_t op, int64_t reduce,
     const OptTensor& u, const OptTensor& e, at::IntArrayRef out_feat, at::IntArrayRef lhs_shape, at::IntArrayRef rhs_shape,
     const OptTensor& row_scale, const OptTensor& out_in, int64_t flags, const OptTensor& hub_rows,
-    const OptTensor& hub_seg_ptr, const OptTensor& hub_seg_hub, const OptTensor& hub_light, at::IntArrayRef hub_meta) {
+    const OptTensor& hub_seg_ptr, const OptTensor& hub_seg_hub, const OptTensor& hub_light, const OptTensor& hub_order,
+    at::IntArrayRef hub_meta) {
   const Tensor& ref = u.has_value() ? *u : *e;
   const auto dev = indptr.get_device();
   const int64_t n_rows = indptr.numel() - 1, nnz = indices.numel();
@@ -180,8 +189,8 @@ std::tuple<Tensor, Tensor, Tensor> gspmm(
   }
   dglb_hub_t hub;
   Tensor ws;
-  const bool has_hub = make_hub(&hub, hub_rows, hub_seg_ptr, hub_seg_hub, hub_light, hub_meta);
-  if (has_hub) {
+  const bool has_hub = make_hub(&hub, hub_rows, hub_seg_ptr, hub_seg_hub, hub_light, hub_meta, hub_order);
+  if (has_hub && hub.n_hub > 0) {
     const size_t need = dglb_hub_workspace_bytes(hub.n_seg, prod(out_feat), cmp ? 1 : 0);
     ws = at::empty({(int64_t)std::max<size_t>(need, 4)}, ref.options().dtype(at::kByte));
     hub.workspace = ws.data_ptr(); hub.workspace_bytes = need;
@@ -205,14 +214,14 @@ Tensor gsddmm_csr(const Tensor& indptr, const Tensor& indices, const OptTensor& 
                   int64_t lhs_target, int64_t rhs_target, const OptTensor& lhs, const OptTensor& rhs,
                   at::IntArrayRef out_feat, at::IntArrayRef lhs_shape, at::IntArrayRef rhs_shape, const OptTensor& hub_rows,
                   const OptTensor& hub_seg_ptr, const OptTensor& hub_seg_hub, const OptTensor& hub_light,
-                  at::IntArrayRef hub_meta) {
+                  const OptTensor& hub_order, at::IntArrayRef hub_meta) {
   const Tensor& ref = lhs.has_value() ? *lhs : *rhs;
   const auto dev = indptr.get_device();
   const int64_t n_dst = indptr.numel() - 1, nnz = indices.numel();
   Tensor out = at::empty(with_rows(nnz, out_feat), ref.options());
   if (nnz == 0 || out.numel() == 0) return out;
   dglb_hub_t hub;
-  const bool has_hub = make_hub(&hub, hub_rows, hub_seg_ptr, hub_seg_hub, hub_light, hub_meta);
+  const bool has_hub = make_hub(&hub, hub_rows, hub_seg_ptr, hub_seg_hub, hub_light, hub_meta, hub_order);
   Entered en(indptr);
   check_status(dglb_gsddmm_csr((int)op, dtype_code(ref), (int)lhs_target, (int)rhs_target, n_dst, n_src, nnz,
                                i32(indptr, "indptr"), i32(indices, "indices"), i32_opt(eids, "eids"),
@@ -509,10 +518,10 @@ TORCH_LIBRARY(dglb200, m) {
   m.def("edge_stage(Tensor stage_pos, Tensor t, bool to_staged) -> Tensor", &edge_stage);
   m.def("gspmm(Tensor indptr, Tensor indices, Tensor? eids, int n_cols, int op, int reduce, Tensor? u, Tensor? e, "
         "int[] out_feat, int[] lhs_shape, int[] rhs_shape, Tensor? row_scale, Tensor? out, int flags, Tensor? hub_rows, "
-        "Tensor? hub_seg_ptr, Tensor? hub_seg_hub, Tensor? hub_light, int[] hub_meta) -> (Tensor, Tensor, Tensor)", &gspmm);
+        "Tensor? hub_seg_ptr, Tensor? hub_seg_hub, Tensor? hub_light, Tensor? hub_order, int[] hub_meta) -> (Tensor, Tensor, Tensor)", &gspmm);
   m.def("gsddmm_csr(Tensor indptr, Tensor indices, Tensor? eids, int n_src, int op, int lhs_target, int rhs_target, "
         "Tensor? lhs, Tensor? rhs, int[] out_feat, int[] lhs_shape, int[] rhs_shape, Tensor? hub_rows, Tensor? hub_seg_ptr, "
-        "Tensor? hub_seg_hub, Tensor? hub_light, int[] hub_meta) -> Tensor", &gsddmm_csr);
+        "Tensor? hub_seg_hub, Tensor? hub_light, Tensor? hub_order, int[] hub_meta) -> Tensor", &gsddmm_csr);
   m.def("gsddmm_coo(Tensor src, Tensor dst, int n_src, int n_dst, int op, int lhs_target, int rhs_target, Tensor? lhs, "
         "Tensor? rhs, int[] out_feat, int[] lhs_shape, int[] rhs_shape) -> Tensor", &gsddmm_coo);
   m.def("edge_softmax_fwd(Tensor indptr, Tensor? eids, Tensor logits, int heads, Tensor? hub_rows, Tensor? hub_seg_ptr, "

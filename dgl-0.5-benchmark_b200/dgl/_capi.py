@@ -44,7 +44,7 @@ class HubStruct(ctypes.Structure):
     _fields_ = [("rows", ctypes.c_void_p), ("seg_ptr", ctypes.c_void_p), ("seg_hub", ctypes.c_void_p),
                 ("n_hub", ctypes.c_int32), ("n_seg", ctypes.c_int32), ("seg_len", ctypes.c_int32),
                 ("threshold", ctypes.c_int32), ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
-                ("light_indptr", ctypes.c_void_p)]
+                ("light_indptr", ctypes.c_void_p), ("row_order", ctypes.c_void_p)]
 
 
 _hub_t = ctypes.POINTER(HubStruct)
@@ -155,7 +155,7 @@ def call(fn, *args):
         raise DGLError(str(ex).split("\n")[0]) from None
 
 
-NO_HUB = (None, None, None, None, [])
+NO_HUB = (None, None, None, None, None, [])
 
 
 def check(rc, what):

@@ -19,7 +19,7 @@ class CSRView:
     """indptr / indices / eids (None == identity) over `n_rows` rows, all int32 device tensors,
     plus per-threshold hub-row lists (caller-owned metadata of the C-ABI)."""
 
-    __slots__ = ("n_rows", "n_cols", "indptr", "indices", "eids", "_hubs", "_deg", "_deg_f", "_stage", "max_deg")
+    __slots__ = ("n_rows", "n_cols", "indptr", "indices", "eids", "_hubs", "_deg", "_deg_f", "_stage", "max_deg", "_order")
 
     LOG2_STAGE_BUCKET = 15  # staged edge order: slots are shuffled inside windows of 32 K CSR positions
 
@@ -31,6 +31,14 @@ class CSRView:
         self._deg_f = None
         self._stage = None
         self.max_deg = None   # largest row length when it is known from the host side (graphs built from CPU tensors)
+        self._order = None
+
+    def row_order(self):
+        """Row ids by non-increasing nnz (stable), int32: the degree-ordered hand-out of rows to the row-per-group
+        kernels (dglb_hub_t.row_order).  Built once per view, on the device."""
+        if self._order is None:
+            self._order = torch.argsort(self.degrees(), descending=True, stable=True).to(torch.int32)
+        return self._order
 
     def stage_plan(self):
         """(stage_pos by edge id, slot by CSR position) of the staged edge order (include/dglb200.h,
@@ -98,9 +106,9 @@ class HubInfo:
         self.light_indptr = light_indptr
 
     def pack(self):
-        """The hub arguments of the extension's ops: (rows, seg_ptr, seg_hub, light_indptr, [n_hub, n_seg, seg_len,
-        threshold]); workspaces are allocated by the op."""
-        return (self.rows, self.seg_ptr, self.seg_hub, self.light_indptr,
+        """The hub arguments of the extension's ops: (rows, seg_ptr, seg_hub, light_indptr, row_order slot, [n_hub, n_seg,
+        seg_len, threshold]); workspaces are allocated by the op; the row order is filled in by the caller."""
+        return (self.rows, self.seg_ptr, self.seg_hub, self.light_indptr, None,
                 [self.n_hub, self.n_seg, self.seg_len, self.threshold])
 
     def struct(self, workspace=None):

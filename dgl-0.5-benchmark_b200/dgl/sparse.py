@@ -7,6 +7,7 @@ same "skip the kernel when the graph has no edges" rule.  Outputs are allocated 
 everything else happens in lib/libdglb200.so on the current CUDA stream.
 """
 import ctypes
+import os
 
 import torch
 
@@ -28,9 +29,21 @@ def _hub_threshold(width, row_cta=False):
     return _capi.ops().default_hub_threshold(1 if row_cta else 0, int(width))
 
 
-def _hub_pack(info):
+# Degree-ordered hand-out of rows to the row-per-group kernels of gspmm / gsddmm (dglb_hub_t.row_order): "auto" = on
+# graphs that have hub rows (skewed degrees: the 4-32 rows a warp walks together differ wildly in length otherwise),
+# "always", "never".  Results are bit-identical either way.
+ROW_ORDER = os.environ.get("DGLB_ROW_ORDER", "auto")
+
+
+def _hub_pack(info, view=None):
     """(hub arguments of an extension op, extra launches the hub path adds)."""
-    return (_capi.NO_HUB, 0) if info is None else (info.pack(), 1)
+    order = None
+    if view is not None and (ROW_ORDER == "always" or (ROW_ORDER == "auto" and info is not None)):
+        order = view.row_order()
+    if info is None:
+        return ((None, None, None, None, order, []) if order is not None else _capi.NO_HUB), 0
+    p = info.pack()
+    return (p[0], p[1], p[2], p[3], order, p[5]), 1
 
 
 # Staged edge order (include/dglb200.h, dglb_edge_stage_plan): on graphs whose CSC / CSR carries a non-trivial edge-id
@@ -190,7 +203,7 @@ def _gspmm(gidx, op, reduce_op, u, e, row_scale=None, out=None, zero_inf=False):
         # once for all R relations; it has no split-row path, so no hub rows are handed to it
         rel = (op == "mul" and not use_cmp and out is None and dtype == _capi.F32 and u.dim() == 3 and e.dim() == 3
                and u.shape[1] == 1 and e.shape[2] == 1 and e.shape[1] in (2, 4, 8) and 1 < u.shape[2] <= 128)
-        hub, hub_launches = (_capi.NO_HUB, 0) if rel else _hub_pack(csc.hubs(_hub_threshold(out_len)))
+        hub, hub_launches = (_capi.NO_HUB, 0) if rel else _hub_pack(csc.hubs(_hub_threshold(out_len)), csc)
         if hub_launches:
             hub_launches = 2          # segment kernel + combine kernel
         ndim, ls, rs = _shapes_for_abi(op, u, e)
@@ -273,7 +286,7 @@ def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
             width = 1
             for s_ in ref.shape[1:]:
                 width *= s_
-            hub, hub_launches = _hub_pack(csc.hubs(_hub_threshold(width)))
+            hub, hub_launches = _hub_pack(csc.hubs(_hub_threshold(width)), csc)
             # narrow results (u_dot_v, u_add_v on (N,H,1) scores) on a shuffled graph: the kernel writes them in
             # staged order (stores stay inside a 32 K-slot window), one pass then puts them in edge-id order
             plan = None
@@ -305,7 +318,7 @@ def _softmax_hub(csc, heads):
     if info is None or heads > 32:
         return (None, None, None, []), 0
     p = info.pack()
-    return (p[0], p[1], p[2], p[4]), 3
+    return (p[0], p[1], p[2], p[5]), 3
 
 
 def _edge_softmax_fwd(gidx, logits):
@@ -361,7 +374,7 @@ def _gat_hub(view, H, F, launches):
     if info is None:
         return (None, None, None, []), 0
     p = info.pack()
-    return (p[0], p[1], p[2], p[4]), (launches if GAT_HUB_SEGMENTS else 1)
+    return (p[0], p[1], p[2], p[5]), (launches if GAT_HUB_SEGMENTS else 1)
 
 
 def _gat_fwd(gidx, ft, el, er, slope, dropout_p, seed, want_scores=False, eids=None):

@@ -134,6 +134,11 @@ int32_t dglb_default_softmax_hub_threshold(int64_t n_heads);
  *                       persistent ring kernels (wide-row gspmm copy_lhs/sum, gsddmm u_dot_v) cut the rows into equal
  *                       shares of THEIR work with it; without it they balance on indptr, which on a hub-heavy graph
  *                       leaves the warps whose range is mostly hub edges idle (2x on a power-law reddit shape)
+ *   row_order [n_rows]  (optional, may be NULL) the row ids sorted by non-increasing nnz (stable).  The row-per-group
+ *                       kernels of gspmm / gsddmm then hand the k-th group of lanes row_order[k] instead of row k: the
+ *                       4-32 rows a warp walks together have (nearly) equal lengths, so no group idles until the
+ *                       warp's longest row is done, and the longest rows start first (degree-binned nnz balance; every
+ *                       row is still summed by one group in CSR order: results are bit-identical with or without it)
  * All arrays are device pointers owned by the caller. */
 typedef struct dglb_hub_t {
   const int32_t* rows;
@@ -143,6 +148,7 @@ typedef struct dglb_hub_t {
   void* workspace;
   size_t workspace_bytes;
   const int32_t* light_indptr;
+  const int32_t* row_order;
 } dglb_hub_t;
 size_t dglb_hub_workspace_bytes(int64_t n_seg, int64_t out_len, int with_args);
 
