@@ -477,7 +477,7 @@ def main():
         launches = int(cnt.item())
     # ---- blocks outside the headline sweep (every rank takes part in the epoch block's collectives)
     peak, peak_src = measured_peak()
-    secondary = parity = epochs = None
+    secondary = parity = epochs = small = None
     if not args.no_extras:
         import bench_extras
         if world == 1:
@@ -489,6 +489,9 @@ def main():
             feats = host = host_out = g = part = None
             torch.cuda.empty_cache()
             epochs = bench_extras.epochs_block(rank, world, dev, epochs=max(4, args.epochs))
+            if world == 1:
+                torch.cuda.empty_cache()
+                small = bench_extras.small_graph_block(dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -532,6 +535,8 @@ def main():
         line["parity"] = parity
     if epochs is not None:
         line["epochs"] = epochs
+    if small is not None:
+        line["small_graphs"] = small
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_arm(1, 0, budget_s=15.0)
         line["cpu_baseline"] = cb

@@ -256,6 +256,9 @@ int dglb_gsddmm_coo(int op, int dtype, int lhs_target, int rhs_target, int64_t n
   DGLB_CHECK_ARG((src && dst) || nnz == 0, "gsddmm_coo: null src/dst");
   if (dtype != DGLB_F32) { set_error("gsddmm_coo: only f32 is implemented"); return DGLB_E_UNSUPPORTED; }
   if (nnz == 0) return DGLB_OK;
+  rc = sddmm_coo_narrow_f32(op, lhs_target, rhs_target, nnz, src, dst, static_cast<const float*>(lhs),
+                            static_cast<const float*>(rhs), b, rs, static_cast<float*>(out), static_cast<cudaStream_t>(stream));
+  if (rc != DGLB_E_UNSUPPORTED) return rc;   // rows of <= 8 floats with equal shapes: one thread per edge
   GenericSddmmParams g;
   g.src = src; g.dst = dst; g.indptr = nullptr; g.indices = nullptr; g.eids = nullptr;
   g.L = static_cast<const float*>(lhs); g.R = static_cast<const float*>(rhs); g.out = static_cast<float*>(out);

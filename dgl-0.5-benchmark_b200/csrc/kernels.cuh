@@ -83,6 +83,9 @@ int ring_rows(bool dot, int dtype, int64_t n_rows, int64_t n_cols, int64_t nnz, 
               const float* row_scale, int accumulate, int hub_threshold, const int32_t* light_indptr,
               cudaStream_t stream);
 int sddmm_generic_f32(const GenericSddmmParams& g, cudaStream_t stream);
+int sddmm_coo_narrow_f32(int op, int lhs_target, int rhs_target, int64_t nnz, const int32_t* src, const int32_t* dst,
+                         const float* L, const float* R, const BcastShape& b, int64_t reduce_size, float* out,
+                         cudaStream_t stream);
 // edge_stage.cu
 size_t edge_stage_plan_workspace_bytes(int64_t nnz, int log2_bucket);
 int edge_stage_plan(int64_t nnz, const int32_t* eids, int log2_bucket, int32_t* stage_pos, int32_t* slot,

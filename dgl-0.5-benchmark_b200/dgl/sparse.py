@@ -57,6 +57,7 @@ STAGE_MIN_BYTES = 96 << 20
 # operands / results gain 1.3-2.5x, (E,4) ones lose 5-8 % in gspmm / gsddmm (a 16-byte access already uses half a
 # sector pair) but still gain 1.2x in edge_softmax.  A second pass that brings the tensor all the way into CSR-position
 # order (so the kernels run with eids = NULL) was measured too and loses to the single staging pass everywhere.
+NARROW_COO_MAX_FLOATS = int(os.environ.get("DGLB_NARROW_COO", "8"))   # 0 disables (A/B measurements)
 STAGE_MAX_ROW_FLOATS = 2
 STAGE_MAX_ROW_FLOATS_SOFTMAX = 8
 
@@ -281,6 +282,16 @@ def _gsddmm(gidx, op, lhs, rhs, lhs_target="u", rhs_target="v"):
         lt, rt = _TARGET[lhs_target], _TARGET[rhs_target]
         fmts = gidx.formats()
         use_csr = ("csc" in fmts) and ((lhs_target == "u" and rhs_target == "v") or "coo" not in fmts)
+        # rows of <= NARROW_COO_MAX_FLOATS floats with the same shape on both sides (attention logits, (N,1) scores):
+        # one thread per edge over the COO -- coalesced ids and results in edge-id order, no permutation, L2-resident
+        # gathers (csrc/sddmm.cu sddmm_coo_narrow_kernel); the destination-major kernel is for wide rows
+        if use_csr and "coo" in fmts and dtype == _capi.F32 and NARROW_COO_MAX_FLOATS > 0:
+            same = (not (use_lhs and use_rhs)) or tuple(lhs.shape[1:]) == tuple(rhs.shape[1:])
+            row_floats = 1
+            for s_ in ref.shape[1:]:
+                row_floats *= s_
+            if same and row_floats <= NARROW_COO_MAX_FLOATS and (op != "dot" or ref.dim() == 2):
+                use_csr = False
         if use_csr:
             csc = gidx.csc()
             width = 1
