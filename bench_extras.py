@@ -239,7 +239,7 @@ def epochs_block(rank, world, dev, epochs=9, configs=None):
         r = epoch_bench.run_config(name, epochs, rank, world, dev, "uniform")
         res[name] = {k: r[k] for k in ("epoch_s", "epoch_s_min", "epochs_timed", "nodes", "edges", "n_gpus",
                                        "sparse_launches_per_epoch", "v100_dgl_epoch_s_published", "loss_first",
-                                       "loss_last")}
+                                       "loss_last", "step_launch")}
         torch.cuda.empty_cache()
     return res
 

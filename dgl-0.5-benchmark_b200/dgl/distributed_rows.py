@@ -313,6 +313,28 @@ class RowPartition:
                 gbuf.record_stream(st)
         return [(gbuf, ev) for gbuf, ev in zip(gbufs, all_events)]
 
+
+    def p2p_all_reduce_flat(self, flat):
+        """Sum of a small 1-D float tensor over the ranks through symmetric memory (publish, two device barriers, every
+        rank adds the P published vectors in rank order): identical bits on every rank, no NCCL kernel, capturable in a
+        CUDA graph next to the exchanges above.  Meant for the dense parameter gradients + loss of a full-graph epoch
+        (tens of KB); the first call per length is a collective (rendezvous)."""
+        key = ("flat", int(flat.numel()), flat.dtype)
+        if key not in self._p2p:
+            import torch.distributed._symmetric_memory as symm_mem
+            t = symm_mem.empty((int(flat.numel()),), dtype=flat.dtype, device=flat.device)
+            hdl = symm_mem.rendezvous(t, self._p2p_group)
+            views = [hdl.get_buffer(r, (int(flat.numel()),), flat.dtype) if r != self.rank else t for r in range(self.world)]
+            self._p2p[key] = (t, hdl, views)
+        t, hdl, views = self._p2p[key]
+        hdl.barrier(channel=0)          # every peer has finished reading what the buffer held before
+        t.copy_(flat)
+        hdl.barrier(channel=1)          # every rank has published
+        out = views[0].clone()
+        for r in range(1, self.world):
+            out += views[r]
+        return out
+
     @staticmethod
     def _wait(events, upto):
         pending = [events[k] for k in range(1, upto + 1) if events[k] is not None]

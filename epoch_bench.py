@@ -45,6 +45,50 @@ CONFIGS = {
 }
 
 
+def _capture_epoch(model, part, feats, labels, train_idx, n_train_total, kw, dev):
+    """(replay, static loss tensor) of one full SAGE training epoch on a RowPartition captured as a CUDA graph, or None
+    when the capture fails on this rank (the caller then falls back to eager launches on every rank)."""
+    try:
+        opt = torch.optim.Adam(model.parameters(), lr=kw["lr"], weight_decay=kw["wd"], capturable=True)
+        params = [p for p in model.parameters()]
+        static_loss = torch.zeros((), device=dev)
+
+        def body():
+            model.train()
+            out = model(part, feats)
+            loss = F.cross_entropy(out[train_idx], labels[train_idx], reduction="sum") / n_train_total
+            loss.backward()
+            flat = torch.cat([p.grad.reshape(-1) for p in params] + [loss.detach().reshape(1)])
+            tot = part.p2p_all_reduce_flat(flat)
+            off = 0
+            for p in params:
+                p.grad.copy_(tot[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            static_loss.copy_(tot[off])
+            opt.step()
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):                       # warm-up on a side stream, as torch's capture recipe asks
+                opt.zero_grad(set_to_none=True)
+                body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        cg = torch.cuda.CUDAGraph()
+        opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(cg):
+            body()
+        return cg.replay, static_loss
+    except Exception as ex:   # noqa: BLE001
+        sys.stderr.write("[epoch_bench] CUDA-graph capture of the epoch failed (%s); eager launches\n" % str(ex).split("\n")[0])
+        try:
+            torch.cuda.synchronize()
+        except Exception:   # noqa: BLE001
+            pass
+        return None
+
+
 def run_config(name, epochs, rank, world, dev, degree, unfused=False):
     shape, kind, kw, v100 = CONFIGS[name]
     (n, src, dst), feats, labels, train_idx, n_classes = synthetic_task(
@@ -101,6 +145,22 @@ def run_config(name, epochs, rank, world, dev, degree, unfused=False):
             dist.all_reduce(loss)
         losses.append(loss.item())       # synchronises, like the OGB scripts (main_dgl_arxiv_gat.py:74)
 
+    step_launch = "eager"
+    if world > 1 and kind == "sage" and getattr(graph, "p2p", False) and os.environ.get("DGLB_EPOCH_GRAPH", "1") != "0":
+        # The partitioned epoch is launch-bound from Python (8 GPUs: ~300 launches around 5 ms of kernels): capture the
+        # whole epoch -- exchanges, aggregation, dense layers, gradient all-reduce (through symmetric memory, so no NCCL
+        # kernel sits inside the graph), Adam -- once and replay it.  SAGE only: the fused GAT kernels take their
+        # attention-dropout seed by value, which a replay would freeze.  Every rank must agree on the outcome.
+        captured = _capture_epoch(model, graph, feats, labels, train_idx, n_train_total, kw, dev)
+        ok = torch.tensor([1.0 if captured is not None else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 1.0:
+            replay, static_loss = captured
+            step_launch = "cuda-graph replay"
+
+            def step():   # noqa: F811
+                replay()
+                losses.append(static_loss.item())   # synchronises once per epoch, like the eager step
     l0 = _capi.launches()
     mean_s, dur = time_epochs(step, epochs)
     launches = (_capi.launches() - l0) / epochs
@@ -112,7 +172,7 @@ def run_config(name, epochs, rank, world, dev, degree, unfused=False):
             "epoch_s": mean_s, "epoch_s_min": float(np.min(dur)), "epochs_timed": len(dur),
             "v100_dgl_epoch_s_published": v100, "sparse_launches_per_epoch": launches,
             "loss_first": losses[0], "loss_last": losses[-1], "degree": degree,
-            "gat_fused": (kind == "gat" and not unfused), "data": "synthetic"}
+            "gat_fused": (kind == "gat" and not unfused), "step_launch": step_launch, "data": "synthetic"}
 
 
 def main():
