@@ -210,7 +210,10 @@ constexpr int spmm_min_ctas(int rmode, int ch, int vec) {
   return 0;
 }
 
-template <int VEC, int CH, int OP, int RED, int RMODE, typename T = float>
+// ORDERED: rows are handed out through p.row_order.  A separate instantiation, so that the natural-order kernels keep
+// exactly the code (and the gather batching ptxas gives it, tests/test_sass_load_batching.py) they had before: with a
+// runtime `if (p.row_order)` in the one kernel ptxas split the 8-gather batch of the scalar-weight variant into 3 + 5.
+template <int VEC, int CH, int OP, int RED, int RMODE, typename T = float, bool ORDERED = false>
 __global__ void __launch_bounds__(kBlockThreads, spmm_min_ctas<OP, RED>(RMODE, CH, VEC))
 spmm_rows_kernel(const SpmmParams p) {
   const int G = p.G;
@@ -220,14 +223,14 @@ spmm_rows_kernel(const SpmmParams p) {
   bool active = row < p.n_rows;
   if (active) {
     // degree-ordered hand-out: the groups of a warp get rows of (nearly) equal length, longest rows first
-    if (p.row_order) row = __ldg(p.row_order + row);
+    if constexpr (ORDERED) row = __ldg(p.row_order + row);
     row_start = __ldg(p.indptr + row);
     deg = __ldg(p.indptr + row + 1) - row_start;
     if (deg > p.hub_threshold) { active = false; deg = 0; }  // left to the hub kernel
   }
-  const int nmax = __reduce_max_sync(FULL_MASK, deg);
   float scale = 1.f;
   if (p.row_scale && active) scale = __ldg(p.row_scale + row);
+  const int nmax = __reduce_max_sync(FULL_MASK, deg);
   for (int tile0 = 0; tile0 < p.ncols; tile0 += G * CH) {
     Acc<VEC, CH, RED> acc;
     acc.init();
@@ -546,7 +549,8 @@ static int launch_fast(const SpmmParams& p, int n_hub, int n_seg, cudaStream_t s
   const int rows_per_block = kBlockThreads / p.G;
   const int64_t blocks = (p.n_rows + rows_per_block - 1) / rows_per_block;
   if (blocks > 0 && !p.skip_rows) {
-    spmm_rows_kernel<VEC, CH, OP, RED, RMODE, T><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+    if (p.row_order) spmm_rows_kernel<VEC, CH, OP, RED, RMODE, T, true><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
+    else spmm_rows_kernel<VEC, CH, OP, RED, RMODE, T, false><<<(unsigned)blocks, kBlockThreads, 0, stream>>>(p);
     DGLB_LAUNCH_CHECK("spmm_rows_kernel");
   }
   if (n_hub > 0 && n_seg > 0) {

@@ -11,16 +11,16 @@ import pytest
 from conftest import ROOT
 
 KERNELS = {  # mangled-name fragment -> minimum run of vector loads with no FP instruction in between
-    "spmm_rows_kernelILi2ELi4ELi4ELi0ELi0EfEE": 6,        # gspmm copy_u_sum, D=602 (LDG.64)
-    "spmm_rows_kernelILi4ELi1ELi4ELi0ELi0EfEE": 6,        # gspmm copy_u_sum, D=64..128 (LDG.128)
-    "spmm_rows_kernelILi4ELi2ELi4ELi0ELi0EfEE": 6,        # D=256
+    "spmm_rows_kernelILi2ELi4ELi4ELi0ELi0EfLb0EEE": 6,        # gspmm copy_u_sum, D=602 (LDG.64)
+    "spmm_rows_kernelILi4ELi1ELi4ELi0ELi0EfLb0EEE": 6,        # gspmm copy_u_sum, D=64..128 (LDG.128)
+    "spmm_rows_kernelILi4ELi2ELi4ELi0ELi0EfLb0EEE": 6,        # D=256
     "sddmm_dot_kernelILi2ELi4ELi5ELb0ELb0EfEE": 8,        # gsddmm u_dot_v, D=602
     "sddmm_dot_kernelILi4ELi1ELi4ELb1ELb0EfEE": 6,        # D=64
     "sddmm_dot_kernelILi4ELi2ELi5ELb1ELb0EfEE": 6,        # D=256
-    "spmm_rows_kernelILi8ELi4ELi4ELi0ELi0E13__nv_bfloat16": 6,  # bf16 storage, D=608
+    "spmm_rows_kernelILi8ELi4ELi4ELi0ELi0E13__nv_bfloat16Lb0E": 6,  # bf16 storage, D=608
     # u_mul_e_sum with (E,1) weights, D=64: the weight shuffles are hoisted in front of the gathers; with them in
     # the consume phase ptxas issued the batch as 3 + 5 gathers
-    "spmm_rows_kernelILi4ELi1ELi2ELi0ELi3EfEE": 7,
+    "spmm_rows_kernelILi4ELi1ELi2ELi0ELi3EfLb0EEE": 7,
 }
 
 
@@ -63,12 +63,12 @@ def test_gathers_are_issued_as_a_batch(sass, fragment, min_run):
 # products graph: copy_u_sum 2.72 ms at 70 registers vs 4.78 ms at 84; copy_u_max 4.04 ms at 98 vs 2.88 ms
 # at 80; fused GAT 1.2-1.35x from 2 -> 3 CTAs per SM (profiles/r01_notes.md sections 9-10).
 REG_BUDGET = {
-    "spmm_rows_kernelILi4ELi1ELi4ELi0ELi0EfEE": 80,   # copy_u_sum D=64/128
-    "spmm_rows_kernelILi4ELi2ELi4ELi0ELi0EfEE": 80,   # D=256
-    "spmm_rows_kernelILi2ELi4ELi4ELi0ELi0EfEE": 80,   # D=602
-    "spmm_rows_kernelILi4ELi1ELi4ELi1ELi0EfEE": 80,   # copy_u_max D=64
-    "spmm_rows_kernelILi2ELi4ELi4ELi1ELi0EfEE": 80,   # copy_u_max D=602
-    "spmm_rows_kernelILi4ELi1ELi2ELi0ELi3EfEE": 80,   # u_mul_e_sum with (E,1) weights, D=64
+    "spmm_rows_kernelILi4ELi1ELi4ELi0ELi0EfLb0EEE": 80,   # copy_u_sum D=64/128
+    "spmm_rows_kernelILi4ELi2ELi4ELi0ELi0EfLb0EEE": 80,   # D=256
+    "spmm_rows_kernelILi2ELi4ELi4ELi0ELi0EfLb0EEE": 80,   # D=602
+    "spmm_rows_kernelILi4ELi1ELi4ELi1ELi0EfLb0EEE": 80,   # copy_u_max D=64
+    "spmm_rows_kernelILi2ELi4ELi4ELi1ELi0EfLb0EEE": 80,   # copy_u_max D=602
+    "spmm_rows_kernelILi4ELi1ELi2ELi0ELi3EfLb0EEE": 80,   # u_mul_e_sum with (E,1) weights, D=64
     "sddmm_dot_kernelILi2ELi4ELi5ELb0ELb0EfEE": 80,   # u_dot_v D=602
     "gat_fwd_kernelILi4ELi1ELi1ELi4ELi0EEE": 80,      # fused GAT forward, UT = 4, ordinary rows
     "gat_fwd_kernelILi4ELi1ELi4ELi4ELi2EEE": 80,      # ... hub-row segments, 4 heads
