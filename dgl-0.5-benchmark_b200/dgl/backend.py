@@ -205,10 +205,16 @@ def gsddmm(gidx, op, lhs_data, rhs_data, lhs_target="u", rhs_target="v"):
 
 
 def edge_softmax(gidx, logits, eids=None, norm_by="dst"):
-    if eids is not None:
-        raise DGLError("edge_softmax on an edge subset is not supported by the fused kernel")
     if norm_by not in ("dst", "src"):
         raise DGLError("norm_by must be 'src' or 'dst'")
+    if eids is not None:
+        # upstream (python/dgl/backend/pytorch/sparse.py::edge_softmax): softmax inside the edge-induced subgraph that
+        # keeps every node -- `logits` has one row per listed edge, in the order of `eids`
+        from .graph_index import GraphIndex
+        eids = torch.as_tensor(eids, device=gidx.src.device).long().view(-1)
+        if logits.shape[0] != eids.shape[0]:
+            raise DGLError("edge_softmax: expect %d logit rows for the listed edges, got %d" % (eids.shape[0], logits.shape[0]))
+        gidx = GraphIndex(gidx.src[eids].contiguous(), gidx.dst[eids].contiguous(), gidx.n_src, gidx.n_dst, gidx.idtype)
     return EdgeSoftmax.apply(gidx, logits, norm_by)
 
 

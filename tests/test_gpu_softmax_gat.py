@@ -95,6 +95,25 @@ def test_edge_softmax_window_kernel_matches_row_kernel(oracle, cuda, monkeypatch
     np.testing.assert_allclose(n(sums)[deg > 0], 1.0, rtol=1e-5)
 
 
+def test_edge_softmax_on_an_edge_subset(oracle, cuda):
+    """eids != ALL: softmax within the edge-induced subgraph (all nodes kept), logits / result rows in the order of eids
+    (upstream python/dgl/ops/edge_softmax.py); forward and backward against the oracle on that subgraph."""
+    og, g, src, dst = graphs(oracle, 200, 200, 3000, seed=8)
+    rng = np.random.default_rng(8)
+    eids = rng.permutation(3000)[:1200]
+    z = rng.standard_normal((1200, 3)).astype(np.float32)
+    sub = oracle.OracleGraph(src[eids], dst[eids], 200, 200)
+    want = oracle.edge_softmax(sub, z)
+    zt = t(z).requires_grad_(True)
+    got = dgl.ops.edge_softmax(g, zt, eids=torch.from_numpy(eids).to(cuda))
+    np.testing.assert_allclose(n(got), want, rtol=1e-5, atol=1e-30)
+    gout = rng.standard_normal((1200, 3)).astype(np.float32)
+    got.backward(t(gout))
+    np.testing.assert_allclose(n(zt.grad), oracle.edge_softmax_backward(sub, want, gout), rtol=1e-4, atol=1e-6)
+    with pytest.raises(dgl.DGLError):
+        dgl.ops.edge_softmax(g, zt, eids=torch.arange(5, device=cuda))
+
+
 def test_edge_softmax_norm_by_src(oracle, cuda):
     og, g, src, dst = graphs(oracle, 100, 100, 1500, seed=4)
     z = np.random.default_rng(4).standard_normal((1500, 2)).astype(np.float32)
