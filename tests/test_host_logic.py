@@ -159,3 +159,47 @@ def test_bench_byte_model_matches_survey_appendix_c():
     assert abs(bench.sddmm_dot_bytes(n, e, 602, p=0) / 1e9 - 28.6) < 0.1
     assert bench.spmm_bytes(n, e, 602) // e == 2460            # 2 460 B per edge
     assert abs(bench.step_bytes(n, e) / 1e9 - 100.2) < 0.2
+
+
+def test_masked_batchnorm_equals_batchnorm_on_the_real_rows():
+    """examples/small_graph_model.MaskedBatchNorm1d (what lets a padded StaticBatch reproduce the unpadded numbers):
+    with a 0/1 row mask it must give, on the real rows, exactly what nn.BatchNorm1d gives when applied to those rows
+    alone -- outputs, gradients and running statistics, in training and in eval mode."""
+    import torch
+    import sys
+    import os
+    from conftest import ROOT, PKG
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from examples.small_graph_model import MaskedBatchNorm1d
+    torch.manual_seed(0)
+    n_real, n_pad, d = 37, 48, 5
+    x = torch.randn(n_pad, d, dtype=torch.float64)
+    x[n_real:] = 1e3                                        # padding rows hold garbage
+    mask = torch.zeros(n_pad, 1, dtype=torch.float64)
+    mask[:n_real] = 1
+    count = torch.tensor(float(n_real), dtype=torch.float64)
+    ref = torch.nn.BatchNorm1d(d).double()
+    got = MaskedBatchNorm1d(d).double()
+    with torch.no_grad():
+        for m in (ref, got):
+            m.weight.copy_(torch.linspace(0.5, 1.5, d))
+            m.bias.copy_(torch.linspace(-1, 1, d))
+    for step in range(3):
+        xr = (x[:n_real] + step).clone().requires_grad_(True)
+        xg = (x + step).clone().requires_grad_(True)
+        yr = ref(xr)
+        yg = got(xg, mask, count)
+        torch.testing.assert_close(yg[:n_real], yr, rtol=1e-10, atol=1e-10)
+        w = torch.randn(n_real, d, dtype=torch.float64)
+        (yr * w).sum().backward()
+        (yg[:n_real] * w).sum().backward()
+        torch.testing.assert_close(xg.grad[:n_real], xr.grad, rtol=1e-9, atol=1e-10)
+        assert float(xg.grad[n_real:].abs().max()) == 0.0   # padding rows receive no gradient from the real rows' loss
+        torch.testing.assert_close(got.running_mean, ref.running_mean, rtol=1e-10, atol=1e-12)
+        torch.testing.assert_close(got.running_var, ref.running_var, rtol=1e-10, atol=1e-12)
+    assert int(got.num_batches_tracked) == int(ref.num_batches_tracked) == 3
+    ref.eval(); got.eval()
+    torch.testing.assert_close(got(x, mask, count)[:n_real], ref(x[:n_real]), rtol=1e-10, atol=1e-10)
+    torch.testing.assert_close(got(x[:n_real]), ref(x[:n_real]))   # without a mask it IS nn.BatchNorm1d
